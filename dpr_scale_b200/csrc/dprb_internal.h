@@ -1,0 +1,48 @@
+// Internal C++ declarations shared by the kernel translation units of libdprb.so.
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/dprb.h"
+
+namespace dprb {
+
+int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long long lda, long long ldb,
+              long long ldd, int a_mn_major, int b_mn_major, int epilogue, const float* bias, const void* aux,
+              long long ld_aux, void* out2, float alpha, int splits, cudaStream_t stream);
+
+int embed_ln_fwd(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, const float* word,
+                 const float* pos, const float* type, const float* gamma, const float* beta, void* y, float* stats,
+                 int T, int H, int vocab, int max_pos, int type_vocab, float eps, cudaStream_t stream);
+int embed_ln_bwd(const void* dy, const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids,
+                 const float* word, const float* pos, const float* type, const float* gamma, const float* stats,
+                 float* dword, float* dpos, float* dtype, float* dgamma, float* dbeta, int T, int H,
+                 cudaStream_t stream);
+int ln_fwd(const void* z, const float* gamma, const float* beta, void* y, float* stats, float* cls_out,
+           int cls_stride, int T, int H, float eps, cudaStream_t stream);
+int ln_bwd(const void* dy, const float* dy_cls, int cls_stride, const void* z, const float* stats,
+           const float* gamma, void* dz, float* dgamma, float* dbeta, float* dbias, int T, int H,
+           cudaStream_t stream);
+int colsum_bf16(const void* x, long long ld, float* out, int T, int N, cudaStream_t stream);
+
+int attn_fwd_lse(const void* qkv, const int32_t* attn_mask, void* ctx, float* lse, int nseq, int S, int heads,
+                 cudaStream_t stream);
+int attn_bwd_lse(const void* qkv, const int32_t* attn_mask, const void* ctx, const float* lse, const void* dctx,
+                 void* dqkv, int nseq, int S, int heads, cudaStream_t stream);
+
+int score_ce_fwd(const float* q, const float* c, const uint8_t* col_mask, const int64_t* labels, float inv_t,
+                 float* lse, float* loss_sum, float* logits, int Q, int C, int d, cudaStream_t stream);
+int score_ce_bwd(const float* q, const float* c, const float* logits, const int64_t* labels, const float* lse,
+                 float grad_scale, float inv_t, float* dq, float* dc, int Q, int C, int d, int q0, int nq, int c0,
+                 int nc, cudaStream_t stream);
+
+int sumsq_f32(const float* g, long long n, float* out, cudaStream_t stream);
+int adamw_step(float* p, const float* g, float* m, float* v, void* shadow, long long n, float lr, float beta1,
+               float beta2, float eps, float wd, int step, float grad_scale, const float* sumsq, float max_norm,
+               cudaStream_t stream);
+int cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t stream);
+
+long long encoder_workspace_bytes(const dprb_encoder_weights* w, int nseq, int S, int save);
+int encoder_fwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b, float* pooled, cudaStream_t stream);
+int encoder_bwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b, const float* dpooled, int layer_lo,
+                int layer_hi, cudaStream_t stream);
+
+}  // namespace dprb

@@ -1,0 +1,377 @@
+// HBM-bound fused kernels of the encoder: embedding-gather + LayerNorm, LayerNorm fwd/bwd (with the
+// CLS-pooling store / CLS-only upstream gradient fused in), bias-gradient column sums.
+// One warp per token row, 128-bit loads, warp-shuffle reductions, fp32 statistics.
+//
+// Replaces (reference path, via dpr_scale/models/hf_model.py:38):
+//   BertEmbeddings.forward            site-packages/transformers/models/bert/modeling_bert.py:72-112
+//   BertSelfOutput/BertOutput LN      modeling_bert.py:294-298, :352-356
+//   CLS pooling + clone               dpr_scale/models/hf_model.py:39-41
+#include "common.cuh"
+#include "dprb_internal.h"
+
+namespace dprb {
+namespace {
+
+constexpr int WARPS = 8;
+constexpr int THREADS = WARPS * 32;
+
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+  uint4 q = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ void load8f(const float* p, float (&v)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+  uint4 q;
+  q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
+  q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = q;
+}
+__device__ __forceinline__ void store8f(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// mean / rstd of one row held as x[MAXC][8] per lane (inactive chunks hold zeros and are excluded via `act`).
+template <int MAXC>
+__device__ __forceinline__ void row_stats(const float (&x)[MAXC][8], const bool (&act)[MAXC], int H, float eps,
+                                          float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += x[i][j];
+  mean = warp_sum(s) / (float)H;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i)
+    if (act[i]) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { float d = x[i][j] - mean; q += d * d; }
+    }
+  float var = warp_sum(q) / (float)H;
+  rstd = rsqrtf(var + eps);
+}
+
+// ------------------------------------------------------------------ LayerNorm forward
+template <int MAXC, bool EMBED>
+__global__ void __launch_bounds__(THREADS)
+ln_fwd_kernel(const bf16* __restrict__ z, const int64_t* __restrict__ ids, const int64_t* __restrict__ tts,
+              const int64_t* __restrict__ pids, const float* __restrict__ word, const float* __restrict__ pos,
+              const float* __restrict__ type, const float* __restrict__ gamma, const float* __restrict__ beta,
+              bf16* __restrict__ y, float* __restrict__ stats, float* __restrict__ cls_out, int cls_stride, int T,
+              int H, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * WARPS;
+  bool act[MAXC];
+  float g[MAXC][8], b[MAXC][8];
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) {
+    const int c = (lane + 32 * i) * 8;
+    act[i] = c < H;
+    if (act[i]) { load8f(gamma + c, g[i]); load8f(beta + c, b[i]); }
+  }
+  for (int row = warp_global; row < T; row += nwarps) {
+    float x[MAXC][8];
+    if (EMBED) {
+      const long long id = ids[row], tt = tts ? tts[row] : 0, pp = pids[row];
+#pragma unroll
+      for (int i = 0; i < MAXC; ++i) {
+        const int c = (lane + 32 * i) * 8;
+        if (act[i]) {
+          float w[8], p8[8], t8[8];
+          load8f(word + id * H + c, w); load8f(pos + pp * H + c, p8); load8f(type + tt * H + c, t8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[i][j] = (w[j] + t8[j]) + p8[j];  // HF order: (word + type) + pos
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[i][j] = 0.f;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < MAXC; ++i) {
+        const int c = (lane + 32 * i) * 8;
+        if (act[i]) load8(z + (long long)row * H + c, x[i]);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[i][j] = 0.f;
+        }
+      }
+    }
+    float mean, rstd;
+    row_stats<MAXC>(x, act, H, eps, mean, rstd);
+    const bool is_cls = (cls_out != nullptr) && (row % cls_stride == 0);
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      if (act[i]) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (x[i][j] - mean) * rstd * g[i][j] + b[i][j];
+        store8(y + (long long)row * H + c, o);
+        if (is_cls) store8f(cls_out + (long long)(row / cls_stride) * H + c, o);
+      }
+    }
+    if (lane == 0) { stats[2 * (long long)row] = mean; stats[2 * (long long)row + 1] = rstd; }
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm backward
+// Column accumulators (dgamma, dbeta, dbias / type-table grads) live in registers per lane and are
+// flushed once per CTA through shared memory + one atomicAdd per column.
+template <int MAXC>
+__device__ __forceinline__ void flush_cols(float (&acc)[MAXC][8], const bool (&act)[MAXC], float* smem /*[WARPS][H]*/,
+                                           float* __restrict__ out, int H) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i)
+    if (act[i]) {
+      const int c = (lane + 32 * i) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) smem[warp * H + c + j] = acc[i][j];
+    }
+  __syncthreads();
+  for (int c = threadIdx.x; c < H; c += THREADS) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) s += smem[w * H + c];
+    if (s != 0.f) atomicAdd(out + c, s);
+  }
+}
+
+template <int MAXC, bool EMBED>
+__global__ void __launch_bounds__(THREADS)
+ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ dy_cls, int cls_stride,
+              const bf16* __restrict__ z, const int64_t* __restrict__ ids, const int64_t* __restrict__ tts,
+              const int64_t* __restrict__ pids, const float* __restrict__ word, const float* __restrict__ pos,
+              const float* __restrict__ type, const float* __restrict__ stats, const float* __restrict__ gamma,
+              bf16* __restrict__ dz, float* __restrict__ dword, float* __restrict__ dpos, float* __restrict__ dtype,
+              float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int T, int H) {
+  extern __shared__ float smem_f[];
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * WARPS;
+  bool act[MAXC];
+  float g[MAXC][8], ag[MAXC][8], ab[MAXC][8], az[MAXC][8], az1[MAXC][8];
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) {
+    const int c = (lane + 32 * i) * 8;
+    act[i] = c < H;
+    if (act[i]) load8f(gamma + c, g[i]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ag[i][j] = 0.f; ab[i][j] = 0.f; az[i][j] = 0.f; az1[i][j] = 0.f; }
+  }
+  for (int row = warp_global; row < T; row += nwarps) {
+    const bool sparse_dy = (dy_cls != nullptr);
+    if (sparse_dy && (row % cls_stride != 0)) {
+      // upstream gradient is identically zero for this row
+      if (dz != nullptr) {
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i)
+          if (act[i]) *reinterpret_cast<uint4*>(dz + (long long)row * H + (lane + 32 * i) * 8) = make_uint4(0, 0, 0, 0);
+      }
+      continue;
+    }
+    const float mean = stats[2 * (long long)row], rstd = stats[2 * (long long)row + 1];
+    long long id = 0, tt = 0, pp = 0;
+    if (EMBED) { id = ids[row]; tt = tts ? tts[row] : 0; pp = pids[row]; }
+    float xh[MAXC][8], d[MAXC][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      if (act[i]) {
+        float x[8];
+        if (EMBED) {
+          float w[8], p8[8], t8[8];
+          load8f(word + id * H + c, w); load8f(pos + pp * H + c, p8); load8f(type + tt * H + c, t8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = (w[j] + t8[j]) + p8[j];
+        } else {
+          load8(z + (long long)row * H + c, x);
+        }
+        if (sparse_dy) load8f(dy_cls + (long long)(row / cls_stride) * H + c, d[i]);
+        else load8(dy + (long long)row * H + c, d[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i][j] = (x[j] - mean) * rstd;
+          ag[i][j] += d[i][j] * xh[i][j];
+          ab[i][j] += d[i][j];
+          d[i][j] *= g[i][j];  // dxhat
+          s1 += d[i][j];
+          s2 += d[i][j] * xh[i][j];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / (float)H;
+    s2 = warp_sum(s2) / (float)H;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      if (act[i]) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (d[i][j] - s1 - xh[i][j] * s2);
+        if (EMBED) {
+          // scatter-add into the table gradients; the (tiny) type table is accumulated in registers
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            atomicAdd(dword + id * H + c + j, o[j]);
+            atomicAdd(dpos + pp * H + c + j, o[j]);
+            if (tt == 0) az[i][j] += o[j];
+            else if (tt == 1) az1[i][j] += o[j];
+            else atomicAdd(dtype + tt * H + c + j, o[j]);
+          }
+        } else {
+          store8(dz + (long long)row * H + c, o);
+          if (dbias != nullptr) {
+            // accumulate the bf16-rounded value: it is what the downstream GEMMs consume
+#pragma unroll
+            for (int j = 0; j < 8; ++j) az[i][j] += __bfloat162float(__float2bfloat16(o[j]));
+          }
+        }
+      }
+    }
+  }
+  flush_cols<MAXC>(ag, act, smem_f, dgamma, H);
+  flush_cols<MAXC>(ab, act, smem_f, dbeta, H);
+  if (EMBED) {
+    flush_cols<MAXC>(az, act, smem_f, dtype, H);
+    flush_cols<MAXC>(az1, act, smem_f, dtype + H, H);
+  } else if (dbias != nullptr) {
+    flush_cols<MAXC>(az, act, smem_f, dbias, H);
+  }
+}
+
+// ------------------------------------------------------------------ column sums (bias gradients)
+__global__ void __launch_bounds__(THREADS)
+colsum_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ out, int T, int N, int rows_per_cta) {
+  __shared__ float red[WARPS][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(r0 + rows_per_cta, T);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c < N) {
+    for (int r = r0 + warp; r < r1; r += WARPS) {
+      float v[8];
+      load8(x + (long long)r * ld + c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int cc = blockIdx.x * 256 + threadIdx.x;
+  if (threadIdx.x < 256 && cc < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) s += red[w][threadIdx.x];
+    atomicAdd(out + cc, s);
+  }
+}
+
+int grid_for_rows(int T) {
+  int sms = num_sms();
+  if (sms <= 0) sms = 148;
+  long long want = ((long long)T + WARPS - 1) / WARPS;
+  long long cap = (long long)sms * 4;
+  return (int)(want < cap ? want : cap);
+}
+
+}  // namespace
+
+#define DISPATCH_MAXC(H, CALL)                                    \
+  do {                                                            \
+    const int _c = ((H) + 255) / 256;                             \
+    if (_c == 1) { CALL(1); } else if (_c == 2) { CALL(2); }      \
+    else if (_c == 3) { CALL(3); } else { CALL(4); }              \
+  } while (0)
+
+static int check_h(int H, const char* who) {
+  DPRB_REQUIRE(H > 0 && H % 8 == 0 && H <= 1024, "%s: hidden size %d unsupported (need H %% 8 == 0, H <= 1024)", who, H);
+  return 0;
+}
+
+int embed_ln_fwd(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, const float* word,
+                 const float* pos, const float* type, const float* gamma, const float* beta, void* y, float* stats,
+                 int T, int H, int vocab, int max_pos, int type_vocab, float eps, cudaStream_t stream) {
+  if (int rc = check_h(H, "embed_ln_fwd")) return rc;
+  if (T == 0) return 0;
+  (void)vocab; (void)max_pos; (void)type_vocab;
+  const int grid = grid_for_rows(T);
+#define CALL(C) ln_fwd_kernel<C, true><<<grid, THREADS, 0, stream>>>(nullptr, ids, type_ids, pos_ids, word, pos, type, gamma, beta, (bf16*)y, stats, nullptr, 1, T, H, eps)
+  DISPATCH_MAXC(H, CALL);
+#undef CALL
+  DPRB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int ln_fwd(const void* z, const float* gamma, const float* beta, void* y, float* stats, float* cls_out,
+           int cls_stride, int T, int H, float eps, cudaStream_t stream) {
+  if (int rc = check_h(H, "ln_fwd")) return rc;
+  if (T == 0) return 0;
+  DPRB_REQUIRE(cls_out == nullptr || cls_stride > 0, "ln_fwd: cls_stride must be positive");
+  const int grid = grid_for_rows(T);
+#define CALL(C) ln_fwd_kernel<C, false><<<grid, THREADS, 0, stream>>>((const bf16*)z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, gamma, beta, (bf16*)y, stats, cls_out, cls_stride > 0 ? cls_stride : 1, T, H, eps)
+  DISPATCH_MAXC(H, CALL);
+#undef CALL
+  DPRB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int ln_bwd(const void* dy, const float* dy_cls, int cls_stride, const void* z, const float* stats,
+           const float* gamma, void* dz, float* dgamma, float* dbeta, float* dbias, int T, int H,
+           cudaStream_t stream) {
+  if (int rc = check_h(H, "ln_bwd")) return rc;
+  if (T == 0) return 0;
+  DPRB_REQUIRE((dy != nullptr) != (dy_cls != nullptr), "ln_bwd: exactly one of dy / dy_cls must be given");
+  DPRB_REQUIRE(dy_cls == nullptr || cls_stride > 0, "ln_bwd: cls_stride must be positive");
+  const int grid = grid_for_rows(T);
+  const size_t smem = (size_t)WARPS * H * sizeof(float);
+#define CALL(C) ln_bwd_kernel<C, false><<<grid, THREADS, smem, stream>>>((const bf16*)dy, dy_cls, cls_stride > 0 ? cls_stride : 1, (const bf16*)z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stats, gamma, (bf16*)dz, nullptr, nullptr, nullptr, dgamma, dbeta, dbias, T, H)
+  DISPATCH_MAXC(H, CALL);
+#undef CALL
+  DPRB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int embed_ln_bwd(const void* dy, const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids,
+                 const float* word, const float* pos, const float* type, const float* gamma, const float* stats,
+                 float* dword, float* dpos, float* dtype, float* dgamma, float* dbeta, int T, int H,
+                 cudaStream_t stream) {
+  if (int rc = check_h(H, "embed_ln_bwd")) return rc;
+  if (T == 0) return 0;
+  const int grid = grid_for_rows(T);
+  const size_t smem = (size_t)WARPS * H * sizeof(float);
+#define CALL(C) ln_bwd_kernel<C, true><<<grid, THREADS, smem, stream>>>((const bf16*)dy, nullptr, 1, nullptr, ids, type_ids, pos_ids, word, pos, type, stats, gamma, nullptr, dword, dpos, dtype, dgamma, dbeta, nullptr, T, H)
+  DISPATCH_MAXC(H, CALL);
+#undef CALL
+  DPRB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int colsum_bf16(const void* x, long long ld, float* out, int T, int N, cudaStream_t stream) {
+  DPRB_REQUIRE(N % 8 == 0 && ld % 8 == 0, "colsum: N=%d and ld=%lld must be multiples of 8", N, ld);
+  if (T == 0 || N == 0) return 0;
+  int sms = num_sms();
+  if (sms <= 0) sms = 148;
+  const int col_blocks = (N + 255) / 256;
+  int row_chunks = (sms * 4 + col_blocks - 1) / col_blocks;
+  int rows_per_cta = (T + row_chunks - 1) / row_chunks;
+  if (rows_per_cta < 64) rows_per_cta = 64;
+  row_chunks = (T + rows_per_cta - 1) / rows_per_cta;
+  dim3 grid(col_blocks, row_chunks);
+  colsum_kernel<<<grid, THREADS, 0, stream>>>((const bf16*)x, ld, out, T, N, rows_per_cta);
+  DPRB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace dprb

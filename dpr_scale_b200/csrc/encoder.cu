@@ -1,0 +1,187 @@
+// Whole-encoder forward / backward orchestration: the BERT/RoBERTa layer stack as a fixed sequence of
+// dprb kernels on one stream, no host synchronisation, activations saved in a caller-owned workspace.
+//
+// Replaces BertModel.forward (site-packages/transformers/models/bert/modeling_bert.py:628-691, layer
+// loop :440-448, BertLayer :359-421) + CLS pooling of /root/reference/dpr_scale/models/hf_model.py:36-41
+// and the autograd backward Lightning runs after dpr_scale/task/dpr_task.py:153-214.
+// The HF pooler (modeling_bert.py:462-468) is not computed: hf_model.py:39 discards it.
+#include "common.cuh"
+#include "dprb_internal.h"
+
+namespace dprb {
+namespace {
+
+struct Carve {
+  uint8_t* base;
+  long long off;
+  explicit Carve(void* b) : base(reinterpret_cast<uint8_t*>(b)), off(0) {}
+  void* take(long long bytes) {
+    void* p = base ? base + off : nullptr;
+    off += (bytes + 255) & ~255LL;
+    return p;
+  }
+};
+
+struct LayerActs {
+  bf16 *qkv, *ctx, *z1, *x1, *hpre, *hact, *z2, *out;
+  float *lse, *stats1, *stats2;
+};
+
+struct Workspace {
+  bf16* x0;
+  float* emb_stats;
+  int n_layer_slots;
+  LayerActs slot[64];
+  // backward scratch
+  bf16 *gA, *gB, *gH, *gQKV;
+  long long bytes;
+};
+
+int plan(const dprb_encoder_weights* w, int nseq, int S, int save, void* base, Workspace* ws) {
+  DPRB_REQUIRE(w->layers >= 1 && w->layers <= 64, "encoder: layers=%d unsupported", w->layers);
+  DPRB_REQUIRE(w->hidden % 8 == 0 && w->inter % 8 == 0 && w->hidden <= 1024, "encoder: H=%d I=%d unsupported", w->hidden, w->inter);
+  DPRB_REQUIRE(w->heads * 64 == w->hidden, "encoder: head_dim must be 64 (H=%d heads=%d)", w->hidden, w->heads);
+  const long long T = (long long)nseq * S, H = w->hidden, I = w->inter;
+  Carve c(base);
+  ws->x0 = (bf16*)c.take(T * H * 2);
+  ws->emb_stats = (float*)c.take(T * 2 * 4);
+  ws->n_layer_slots = save ? w->layers : 2;
+  for (int i = 0; i < ws->n_layer_slots; ++i) {
+    LayerActs& a = ws->slot[i];
+    a.qkv = (bf16*)c.take(T * 3 * H * 2);
+    a.ctx = (bf16*)c.take(T * H * 2);
+    a.lse = (float*)c.take((long long)nseq * w->heads * S * 4);
+    a.z1 = (bf16*)c.take(T * H * 2);
+    a.stats1 = (float*)c.take(T * 2 * 4);
+    a.x1 = (bf16*)c.take(T * H * 2);
+    a.hpre = save ? (bf16*)c.take(T * I * 2) : nullptr;
+    a.hact = (bf16*)c.take(T * I * 2);
+    a.z2 = (bf16*)c.take(T * H * 2);
+    a.stats2 = (float*)c.take(T * 2 * 4);
+    a.out = (bf16*)c.take(T * H * 2);
+  }
+  if (save) {
+    ws->gA = (bf16*)c.take(T * H * 2);
+    ws->gB = (bf16*)c.take(T * H * 2);
+    ws->gH = (bf16*)c.take(T * I * 2);
+    ws->gQKV = (bf16*)c.take(T * 3 * H * 2);
+  } else {
+    ws->gA = ws->gB = ws->gH = ws->gQKV = nullptr;
+  }
+  ws->bytes = c.off;
+  return 0;
+}
+
+struct LayerW {
+  const bf16 *wqkv, *wo, *w1, *w2;                                  // bf16 shadow
+  const float *bqkv, *bo, *ln1g, *ln1b, *b1, *b2, *ln2g, *ln2b;     // fp32 master
+  float *g_wqkv, *g_bqkv, *g_wo, *g_bo, *g_ln1g, *g_ln1b, *g_w1, *g_b1, *g_w2, *g_b2, *g_ln2g, *g_ln2b;
+};
+
+LayerW layer_w(const dprb_encoder_weights* w, int l) {
+  const long long b = w->off_layer0 + (long long)l * w->layer_stride;
+  const bf16* sh = reinterpret_cast<const bf16*>(w->shadow);
+  const float* ms = w->master;
+  float* gr = w->grads;
+  LayerW r;
+  r.wqkv = sh + b + w->rel_wqkv; r.wo = sh + b + w->rel_wo; r.w1 = sh + b + w->rel_w1; r.w2 = sh + b + w->rel_w2;
+  r.bqkv = ms + b + w->rel_bqkv; r.bo = ms + b + w->rel_bo; r.ln1g = ms + b + w->rel_ln1_g; r.ln1b = ms + b + w->rel_ln1_b;
+  r.b1 = ms + b + w->rel_b1; r.b2 = ms + b + w->rel_b2; r.ln2g = ms + b + w->rel_ln2_g; r.ln2b = ms + b + w->rel_ln2_b;
+  if (gr != nullptr) {
+    r.g_wqkv = gr + b + w->rel_wqkv; r.g_bqkv = gr + b + w->rel_bqkv; r.g_wo = gr + b + w->rel_wo; r.g_bo = gr + b + w->rel_bo;
+    r.g_ln1g = gr + b + w->rel_ln1_g; r.g_ln1b = gr + b + w->rel_ln1_b; r.g_w1 = gr + b + w->rel_w1; r.g_b1 = gr + b + w->rel_b1;
+    r.g_w2 = gr + b + w->rel_w2; r.g_b2 = gr + b + w->rel_b2; r.g_ln2g = gr + b + w->rel_ln2_g; r.g_ln2b = gr + b + w->rel_ln2_b;
+  }
+  return r;
+}
+
+#define TRY(expr) do { if (int _rc = (expr)) return _rc; } while (0)
+
+}  // namespace
+
+long long encoder_workspace_bytes(const dprb_encoder_weights* w, int nseq, int S, int save) {
+  Workspace ws;
+  if (plan(w, nseq, S, save, nullptr, &ws)) return -1;
+  return ws.bytes;
+}
+
+int encoder_fwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b, float* pooled, cudaStream_t stream) {
+  Workspace ws;
+  TRY(plan(w, b->nseq, b->S, b->save_for_backward, b->workspace, &ws));
+  DPRB_REQUIRE(b->workspace != nullptr && b->workspace_bytes >= ws.bytes, "encoder_fwd: workspace too small (%lld < %lld)",
+               (long long)b->workspace_bytes, ws.bytes);
+  DPRB_REQUIRE((reinterpret_cast<uintptr_t>(b->workspace) & 255) == 0, "encoder_fwd: workspace must be 256-byte aligned");
+  const int T = b->nseq * b->S, H = w->hidden, I = w->inter, L = w->layers;
+  if (T == 0) return 0;
+  const float* ms = w->master;
+  TRY(embed_ln_fwd(b->ids, b->type_ids, b->pos_ids, ms + w->off_word, ms + w->off_pos, ms + w->off_type,
+                   ms + w->off_emb_ln_g, ms + w->off_emb_ln_b, ws.x0, ws.emb_stats, T, H, w->vocab, w->max_pos,
+                   w->type_vocab, w->ln_eps, stream));
+  const bf16* x = ws.x0;
+  for (int l = 0; l < L; ++l) {
+    const LayerW lw = layer_w(w, l);
+    LayerActs& a = ws.slot[b->save_for_backward ? l : (l & 1)];
+    TRY(gemm_bf16(x, lw.wqkv, a.qkv, T, 3 * H, H, H, H, 3 * H, 0, 0, DPRB_EPI_BIAS, lw.bqkv, nullptr, 0, nullptr, 1.f, 1, stream));
+    TRY(attn_fwd_lse(a.qkv, b->attn_mask, a.ctx, a.lse, b->nseq, b->S, w->heads, stream));
+    TRY(gemm_bf16(a.ctx, lw.wo, a.z1, T, H, H, H, H, H, 0, 0, DPRB_EPI_BIAS_RESIDUAL, lw.bo, x, H, nullptr, 1.f, 1, stream));
+    TRY(ln_fwd(a.z1, lw.ln1g, lw.ln1b, a.x1, a.stats1, nullptr, 1, T, H, w->ln_eps, stream));
+    TRY(gemm_bf16(a.x1, lw.w1, a.hact, T, I, H, H, H, I, 0, 0, DPRB_EPI_BIAS_GELU, lw.b1, nullptr, 0, a.hpre, 1.f, 1, stream));
+    TRY(gemm_bf16(a.hact, lw.w2, a.z2, T, H, I, I, I, H, 0, 0, DPRB_EPI_BIAS_RESIDUAL, lw.b2, a.x1, H, nullptr, 1.f, 1, stream));
+    const bool last = (l == L - 1);
+    TRY(ln_fwd(a.z2, lw.ln2g, lw.ln2b, a.out, a.stats2, last ? pooled : nullptr, b->S, T, H, w->ln_eps, stream));
+    x = a.out;
+  }
+  return 0;
+}
+
+int encoder_bwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b, const float* dpooled, int layer_lo,
+                int layer_hi, cudaStream_t stream) {
+  Workspace ws;
+  DPRB_REQUIRE(b->save_for_backward, "encoder_bwd: forward was run without save_for_backward");
+  DPRB_REQUIRE(w->grads != nullptr, "encoder_bwd: grads arena is NULL");
+  TRY(plan(w, b->nseq, b->S, 1, b->workspace, &ws));
+  DPRB_REQUIRE(b->workspace != nullptr && b->workspace_bytes >= ws.bytes, "encoder_bwd: workspace too small");
+  const int T = b->nseq * b->S, H = w->hidden, I = w->inter, L = w->layers;
+  DPRB_REQUIRE(0 <= layer_lo && layer_lo < layer_hi && layer_hi <= L, "encoder_bwd: bad layer range [%d,%d)", layer_lo, layer_hi);
+  if (T == 0) return 0;
+  for (int l = layer_hi - 1; l >= layer_lo; --l) {
+    const LayerW lw = layer_w(w, l);
+    LayerActs& a = ws.slot[l];
+    const bf16* x = (l == 0) ? ws.x0 : ws.slot[l - 1].out;
+    const bool last = (l == L - 1);
+    // LN2 backward (+ db2)
+    TRY(ln_bwd(last ? nullptr : ws.gA, last ? dpooled : nullptr, b->S, a.z2, a.stats2, lw.ln2g, ws.gB, lw.g_ln2g,
+               lw.g_ln2b, lw.g_b2, T, H, stream));
+    // dW2 += dz2^T hact
+    TRY(gemm_bf16(ws.gB, a.hact, lw.g_w2, H, I, T, H, I, I, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, stream));
+    // dhpre = (dz2 W2) * gelu'(hpre)
+    TRY(gemm_bf16(ws.gB, lw.w2, ws.gH, T, I, H, H, I, I, 0, 1, DPRB_EPI_DGELU, nullptr, a.hpre, I, nullptr, 1.f, 1, stream));
+    TRY(colsum_bf16(ws.gH, I, lw.g_b1, T, I, stream));
+    // dW1 += dhpre^T x1
+    TRY(gemm_bf16(ws.gH, a.x1, lw.g_w1, I, H, T, I, H, H, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, stream));
+    // dx1 = dhpre W1 + dz2
+    TRY(gemm_bf16(ws.gH, lw.w1, ws.gA, T, H, I, I, H, H, 0, 1, DPRB_EPI_BIAS_RESIDUAL, nullptr, ws.gB, H, nullptr, 1.f, 1, stream));
+    // LN1 backward (+ dbo)
+    TRY(ln_bwd(ws.gA, nullptr, 1, a.z1, a.stats1, lw.ln1g, ws.gB, lw.g_ln1g, lw.g_ln1b, lw.g_bo, T, H, stream));
+    // dWo += dz1^T ctx
+    TRY(gemm_bf16(ws.gB, a.ctx, lw.g_wo, H, H, T, H, H, H, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, stream));
+    // dctx = dz1 Wo
+    TRY(gemm_bf16(ws.gB, lw.wo, ws.gA, T, H, H, H, H, H, 0, 1, DPRB_EPI_BIAS, nullptr, nullptr, 0, nullptr, 1.f, 1, stream));
+    TRY(attn_bwd_lse(a.qkv, b->attn_mask, a.ctx, a.lse, ws.gA, ws.gQKV, b->nseq, b->S, w->heads, stream));
+    TRY(colsum_bf16(ws.gQKV, 3 * H, lw.g_bqkv, T, 3 * H, stream));
+    // dWqkv += dqkv^T x
+    TRY(gemm_bf16(ws.gQKV, x, lw.g_wqkv, 3 * H, H, T, 3 * H, H, H, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, stream));
+    // dx = dqkv Wqkv + dz1
+    TRY(gemm_bf16(ws.gQKV, lw.wqkv, ws.gA, T, H, 3 * H, 3 * H, H, H, 0, 1, DPRB_EPI_BIAS_RESIDUAL, nullptr, ws.gB, H, nullptr, 1.f, 1, stream));
+  }
+  if (layer_lo == 0) {
+    const float* ms = w->master;
+    float* gr = w->grads;
+    TRY(embed_ln_bwd(ws.gA, b->ids, b->type_ids, b->pos_ids, ms + w->off_word, ms + w->off_pos, ms + w->off_type,
+                     ms + w->off_emb_ln_g, ws.emb_stats, gr + w->off_word, gr + w->off_pos, gr + w->off_type,
+                     gr + w->off_emb_ln_g, gr + w->off_emb_ln_b, T, H, stream));
+  }
+  return 0;
+}
+
+}  // namespace dprb

@@ -1,0 +1,163 @@
+"""Tensor-level wrappers over the C ABI (raw device pointers + the current CUDA stream).
+
+PyTorch is plumbing here: device memory, streams, autograd bookkeeping.  Every function launches
+hand-written sm_100a kernels from libdprb.so; nothing falls back to torch math.
+"""
+import torch
+
+from . import _lib
+from ._lib import check
+
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_DGELU, EPI_F32_ATOMIC_ADD, EPI_F32_STORE = range(6)
+
+LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda, "dprb ops need CUDA tensors (no CPU fallback)"
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def gemm(a, b, out, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, epilogue=EPI_BIAS, bias=None, aux=None,
+         ld_aux=0, out2=None, alpha=1.0, splits=1):
+    lib = _lib.load()
+    check(lib.dprb_gemm_bf16(_ptr(a), _ptr(b), _ptr(out), M, N, K, lda, ldb, ldd, int(a_mn), int(b_mn), epilogue,
+                             _ptr(bias), _ptr(aux), ld_aux, _ptr(out2), float(alpha), splits, _stream()),
+          "dprb_gemm_bf16")
+    _count()
+    return out
+
+
+def linear_fwd(x, w, bias=None, epilogue=EPI_BIAS, aux=None, out2=None):
+    """y[T,N] = epi(x[T,K] @ w[N,K]^T + bias); x, w bf16 contiguous; bias fp32."""
+    T, K = x.shape
+    N = w.shape[0]
+    y = torch.empty(T, N, dtype=torch.bfloat16, device=x.device)
+    gemm(x, w, y, T, N, K, K, K, N, False, False, epilogue, bias, aux, N if aux is not None else 0, out2)
+    return y
+
+
+def embed_ln_fwd(ids, type_ids, pos_ids, word, pos, typ, gamma, beta, eps):
+    T = ids.numel()
+    H = word.shape[1]
+    y = torch.empty(T, H, dtype=torch.bfloat16, device=word.device)
+    stats = torch.empty(T, 2, dtype=torch.float32, device=word.device)
+    check(_lib.load().dprb_embed_ln_fwd(_ptr(ids), _ptr(type_ids), _ptr(pos_ids), _ptr(word), _ptr(pos), _ptr(typ),
+                                        _ptr(gamma), _ptr(beta), _ptr(y), _ptr(stats), T, H, word.shape[0],
+                                        pos.shape[0], typ.shape[0], float(eps), _stream()), "dprb_embed_ln_fwd")
+    _count()
+    return y, stats
+
+
+def embed_ln_bwd(dy, ids, type_ids, pos_ids, word, pos, typ, gamma, stats, dword, dpos, dtyp, dgamma, dbeta):
+    T = ids.numel()
+    H = word.shape[1]
+    check(_lib.load().dprb_embed_ln_bwd(_ptr(dy), _ptr(ids), _ptr(type_ids), _ptr(pos_ids), _ptr(word), _ptr(pos),
+                                        _ptr(typ), _ptr(gamma), _ptr(stats), _ptr(dword), _ptr(dpos), _ptr(dtyp),
+                                        _ptr(dgamma), _ptr(dbeta), T, H, _stream()), "dprb_embed_ln_bwd")
+    _count()
+
+
+def ln_fwd(z, gamma, beta, eps, cls_stride=0):
+    T, H = z.shape
+    y = torch.empty_like(z)
+    stats = torch.empty(T, 2, dtype=torch.float32, device=z.device)
+    cls = None
+    if cls_stride:
+        cls = torch.empty((T + cls_stride - 1) // cls_stride, H, dtype=torch.float32, device=z.device)
+    check(_lib.load().dprb_ln_fwd(_ptr(z), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(stats), _ptr(cls),
+                                  cls_stride if cls_stride else 1, T, H, float(eps), _stream()), "dprb_ln_fwd")
+    _count()
+    return y, stats, cls
+
+
+def ln_bwd(dy, z, stats, gamma, dgamma, dbeta, dbias=None, dy_cls=None, cls_stride=1):
+    T, H = z.shape
+    dz = torch.empty_like(z)
+    check(_lib.load().dprb_ln_bwd(_ptr(dy), _ptr(dy_cls), cls_stride, _ptr(z), _ptr(stats), _ptr(gamma), _ptr(dz),
+                                  _ptr(dgamma), _ptr(dbeta), _ptr(dbias), T, H, _stream()), "dprb_ln_bwd")
+    _count()
+    return dz
+
+
+def colsum(x, out):
+    T, N = x.shape
+    check(_lib.load().dprb_colsum_bf16(_ptr(x), x.stride(0), _ptr(out), T, N, _stream()), "dprb_colsum_bf16")
+    _count()
+    return out
+
+
+def attn_fwd(qkv, attn_mask, nseq, S, heads, need_lse=True):
+    T = nseq * S
+    H = heads * 64
+    ctx = torch.empty(T, H, dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty(nseq, heads, S, dtype=torch.float32, device=qkv.device) if need_lse else None
+    check(_lib.load().dprb_attn_fwd(_ptr(qkv), _ptr(attn_mask), _ptr(ctx), _ptr(lse), nseq, S, heads, _stream()),
+          "dprb_attn_fwd")
+    _count()
+    return ctx, lse
+
+
+def attn_bwd(qkv, attn_mask, ctx, lse, dctx, nseq, S, heads):
+    dqkv = torch.empty_like(qkv)
+    check(_lib.load().dprb_attn_bwd(_ptr(qkv), _ptr(attn_mask), _ptr(ctx), _ptr(lse), _ptr(dctx), _ptr(dqkv), nseq,
+                                    S, heads, _stream()), "dprb_attn_bwd")
+    _count()
+    return dqkv
+
+
+def score_ce_fwd(q, c, col_mask, labels, inv_temperature, want_logits=True):
+    Q, d = q.shape
+    C = c.shape[0]
+    lse = torch.empty(Q, dtype=torch.float32, device=q.device)
+    loss_sum = torch.zeros(1, dtype=torch.float32, device=q.device)
+    logits = torch.empty(Q, C, dtype=torch.float32, device=q.device) if want_logits else None
+    check(_lib.load().dprb_score_ce_fwd(_ptr(q), _ptr(c), _ptr(col_mask), _ptr(labels), float(inv_temperature),
+                                        _ptr(lse), _ptr(loss_sum), _ptr(logits), Q, C, d, _stream()),
+          "dprb_score_ce_fwd")
+    _count()
+    return loss_sum, lse, logits
+
+
+def score_ce_bwd(q, c, logits, labels, lse, grad_scale, inv_temperature, q0, nq, c0, nc):
+    Q, d = q.shape
+    C = c.shape[0]
+    dq = torch.empty(nq, d, dtype=torch.float32, device=q.device)
+    dc = torch.empty(nc, d, dtype=torch.float32, device=q.device)
+    check(_lib.load().dprb_score_ce_bwd(_ptr(q), _ptr(c), _ptr(logits), _ptr(labels), _ptr(lse), float(grad_scale),
+                                        float(inv_temperature), _ptr(dq), _ptr(dc), Q, C, d, q0, nq, c0, nc,
+                                        _stream()), "dprb_score_ce_bwd")
+    _count(2)
+    return dq, dc
+
+
+def sumsq(g, out):
+    check(_lib.load().dprb_sumsq_f32(_ptr(g), g.numel(), _ptr(out), _stream()), "dprb_sumsq_f32")
+    _count()
+    return out
+
+
+def adamw_step(p, g, m, v, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, sumsq_buf=None,
+               max_norm=0.0):
+    check(_lib.load().dprb_adamw_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(shadow), p.numel(), float(lr),
+                                      float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
+                                      float(grad_scale), _ptr(sumsq_buf), float(max_norm), _stream()),
+          "dprb_adamw_step")
+    _count()
+
+
+def cast_f32_bf16(src, dst):
+    check(_lib.load().dprb_cast_f32_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()), "dprb_cast_f32_bf16")
+    _count()
+    return dst

@@ -1,0 +1,181 @@
+/* dprb.h — C ABI of libdprb.so: the B200 (sm_100a) drop-in for the arithmetic of dpr-scale's
+ * bi-encoder contrastive training step.
+ *
+ * The reference (facebookresearch/dpr-scale) is pure Python and has no FFI of its own; every FLOP on
+ * the path is delegated to torch / HuggingFace modules.  Each entry point below therefore cites the
+ * reference call site (file:line under /root/reference, or site-packages/transformers for the
+ * third-party code the reference calls) whose arithmetic it replaces.  INTEGRATION.md shows the
+ * ctypes binding a dpr-scale maintainer would add.
+ *
+ * Conventions
+ *  - Every function returns 0 on success; non-zero = error, text via dprb_last_error() (thread-local).
+ *  - All pointers are DEVICE pointers owned by the caller (PyTorch caching allocator); the library
+ *    allocates nothing persistent and keeps no global mutable state besides cached device attributes.
+ *  - `stream` is a cudaStream_t; all work is enqueued on it and no call synchronises the device.
+ *  - bf16 tensors are row-major with 16-byte aligned rows; H, I multiples of 8; head_dim == 64.
+ *  - One process per GPU; collectives are NOT issued here (torch.distributed/NCCL does that).
+ */
+#ifndef DPRB_H_
+#define DPRB_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* dprb_stream_t; /* cudaStream_t */
+
+#define DPRB_VERSION 100
+
+int dprb_version(void);
+const char* dprb_last_error(void);
+/* SM count of the current device (cached); <=0 when no device. */
+int dprb_num_sms(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * GEMM (tcgen05 / TMA / TMEM):  D[M,N] = epilogue( alpha * sum_k A(m,k) * B(n,k) )
+ * Replaces torch.nn.Linear forward/backward inside HF BertLayer:
+ *   site-packages/transformers/models/bert/modeling_bert.py:179-181 (Q,K,V — fused here into one
+ *   [3H,H] weight), :295 (attention output dense), :340 (intermediate dense), :353 (output dense).
+ * a_mn_major/b_mn_major = 0: operand stored [MN, K] (K contiguous, leading dim ld);
+ *                       = 1: operand stored [K, MN] (MN contiguous, leading dim ld).
+ * ------------------------------------------------------------------------------------------- */
+enum {
+  DPRB_EPI_BIAS = 0,           /* D(bf16) = acc + bias                      (bias may be NULL)        */
+  DPRB_EPI_BIAS_GELU = 1,      /* out2(bf16) = acc + bias ; D(bf16) = gelu_erf(out2)                   */
+  DPRB_EPI_BIAS_RESIDUAL = 2,  /* D(bf16) = acc + bias + aux(bf16)                                     */
+  DPRB_EPI_DGELU = 3,          /* D(bf16) = acc * gelu_erf'(aux(bf16))                                 */
+  DPRB_EPI_F32_ATOMIC_ADD = 4, /* D(fp32) += acc  (split-K over `splits` CTAs; 0 = choose)            */
+  DPRB_EPI_F32_STORE = 5,      /* D(fp32) = acc + bias                                                 */
+  DPRB_EPI_COUNT = 6
+};
+int dprb_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int64_t lda, int64_t ldb,
+                   int64_t ldd, int a_mn_major, int b_mn_major, int epilogue, const float* bias,
+                   const void* aux, int64_t ld_aux, void* out2, float alpha, int splits, dprb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Embeddings + LayerNorm.  Replaces BertEmbeddings.forward (modeling_bert.py:72-112):
+ *   z = word[ids] + type[type_ids] + pos[pos_ids];  y = LN(z) (eps, gamma, beta).
+ * Tables and LN parameters are the fp32 master weights.  stats[t] = (mean, rstd).
+ * ------------------------------------------------------------------------------------------- */
+int dprb_embed_ln_fwd(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, const float* word,
+                      const float* pos, const float* type, const float* gamma, const float* beta, void* y_bf16,
+                      float* stats, int T, int H, int vocab, int max_pos, int type_vocab, float eps,
+                      dprb_stream_t stream);
+/* Backward: dz = LN'(dy); dgamma/dbeta accumulated; scatter-add of dz into the three table grads. */
+int dprb_embed_ln_bwd(const void* dy_bf16, const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids,
+                      const float* word, const float* pos, const float* type, const float* gamma,
+                      const float* stats, float* dword, float* dpos, float* dtype, float* dgamma, float* dbeta,
+                      int T, int H, dprb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LayerNorm over rows of z (the residual sum is produced by the preceding GEMM epilogue).
+ * Replaces BertSelfOutput / BertOutput LayerNorm (modeling_bert.py:294-298, :352-356).
+ * If cls_out != NULL, rows t with t % cls_stride == 0 are also written in fp32 to
+ * cls_out[t / cls_stride, :] — the CLS pooling + .clone() of hf_model.py:39-41.
+ * ------------------------------------------------------------------------------------------- */
+int dprb_ln_fwd(const void* z_bf16, const float* gamma, const float* beta, void* y_bf16, float* stats,
+                float* cls_out, int cls_stride, int T, int H, float eps, dprb_stream_t stream);
+/* dz = LN'(dy; z, stats); dgamma += sum dy*xhat; dbeta += sum dy; if dbias != NULL: dbias += sum_t dz
+ * (the bias gradient of the Linear that produced z).  If dy_cls != NULL, dy is implicit: zero
+ * everywhere except rows t % cls_stride == 0 which take dy_cls[t / cls_stride, :] (fp32). */
+int dprb_ln_bwd(const void* dy_bf16, const float* dy_cls, int cls_stride, const void* z_bf16,
+                const float* stats, const float* gamma, void* dz_bf16, float* dgamma, float* dbeta,
+                float* dbias, int T, int H, dprb_stream_t stream);
+
+/* Column sums: out[n] += sum_t x[t, n]  (bias gradients; x bf16 [T, N] with leading dim ld). */
+int dprb_colsum_bf16(const void* x_bf16, int64_t ld, float* out, int T, int N, dprb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Self-attention core for head_dim 64, S <= 256.  Replaces BertSelfAttention.forward's
+ * scaled_dot_product_attention (modeling_bert.py:168-207, integrations/sdpa_attention.py:92-101):
+ *   ctx = softmax(Q K^T / 8 + key_mask) V      per (sequence, head).
+ * qkv: bf16 [nseq*S, 3H] = [Q | K | V] column blocks, head h at columns h*64.
+ * attn_mask: int32 [nseq, S], 1 = real token, 0 = padding (HF attention_mask); may be NULL.
+ * lse: fp32 [nseq, heads, S] natural-log row log-sum-exp, written by fwd (may be NULL for
+ *      forward-only use) and consumed by bwd together with the forward output ctx.
+ * ------------------------------------------------------------------------------------------- */
+int dprb_attn_fwd(const void* qkv_bf16, const int32_t* attn_mask, void* ctx_bf16, float* lse, int nseq, int S,
+                  int heads, dprb_stream_t stream);
+int dprb_attn_bwd(const void* qkv_bf16, const int32_t* attn_mask, const void* ctx_bf16, const float* lse,
+                  const void* dctx_bf16, void* dqkv_bf16, int nseq, int S, int heads, dprb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused in-batch-negative scoring + softmax cross-entropy.
+ * Replaces dpr_scale/task/dpr_task.py:98-105 (sim_score: q @ c.T, scores[mask] = -inf),
+ * :197 (mask.repeat), :211 (scores /= T), :212 (nn.CrossEntropyLoss, mean over Q).
+ *   q fp32 [Q,d], c fp32 [C,d], col_mask u8 [C] (1 = dummy ctx -> -inf), labels i64 [Q].
+ * Outputs: lse[Q], loss_sum (sum over rows of lse - logit[label]; caller divides by Q),
+ *          logits fp32 [Q,C] (masked columns = -inf) if non-NULL; required when backward follows.
+ * Backward of mean-over-Q loss (grad_scale = upstream dL, normally 1):
+ *   dq[q0:q0+nq, :]  (rows owned by this rank)  and  dc[c0:c0+nc, :] (columns owned by this rank),
+ *   reproducing dpr_task.py:163-195 where remote slices are detached constants.
+ * ------------------------------------------------------------------------------------------- */
+int dprb_score_ce_fwd(const float* q, const float* c, const uint8_t* col_mask, const int64_t* labels,
+                      float inv_temperature, float* lse, float* loss_sum, float* logits, int Q, int C, int d,
+                      dprb_stream_t stream);
+int dprb_score_ce_bwd(const float* q, const float* c, const float* logits, const int64_t* labels,
+                      const float* lse, float grad_scale, float inv_temperature, float* dq, float* dc, int Q,
+                      int C, int d, int q0, int nq, int c0, int nc, dprb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Optimizer step over a flat fp32 parameter arena.  Replaces torch.optim.AdamW
+ * (conf/task/optim/adamw.yaml via dpr_task.py:124) + clip_grad_norm_(2.0)
+ * (conf/trainer/gpu_1_host.yaml:8) + the bf16 weight shadow refresh.
+ *   dprb_sumsq: out[0] += sum g^2.
+ *   dprb_adamw_step: coef = min(1, max_norm / (sqrt(*sumsq) * grad_div_inv... see DESIGN.md) applied to g.
+ * ------------------------------------------------------------------------------------------- */
+int dprb_sumsq_f32(const float* g, int64_t n, float* out, dprb_stream_t stream);
+int dprb_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                    const float* sumsq, float max_norm, dprb_stream_t stream);
+/* fp32 -> bf16 shadow refresh (after a state_dict load). */
+int dprb_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, dprb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Whole-encoder forward / backward: the BertModel stack of modeling_bert.py:628-691 as called from
+ * dpr_scale/models/hf_model.py:36-41, minus the unused pooler.  See dprb_encoder.h-style struct below.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  /* dims */
+  int32_t hidden, inter, layers, heads, vocab, max_pos, type_vocab;
+  float ln_eps;
+  /* flat arenas (see dprb_param_offsets): fp32 master, bf16 shadow, fp32 grads */
+  const float* master;
+  const void* shadow;
+  float* grads;
+  /* offsets (in elements) into the arenas */
+  int64_t off_word, off_pos, off_type, off_emb_ln_g, off_emb_ln_b;
+  int64_t off_layer0;     /* first layer block */
+  int64_t layer_stride;   /* elements per layer block */
+  /* per-layer relative offsets */
+  int64_t rel_wqkv, rel_bqkv, rel_wo, rel_bo, rel_ln1_g, rel_ln1_b, rel_w1, rel_b1, rel_w2, rel_b2, rel_ln2_g,
+      rel_ln2_b;
+} dprb_encoder_weights;
+
+typedef struct {
+  int32_t nseq, S;
+  const int64_t* ids;      /* [nseq*S] */
+  const int64_t* type_ids; /* [nseq*S] */
+  const int64_t* pos_ids;  /* [nseq*S] */
+  const int32_t* attn_mask;/* [nseq*S] or NULL */
+  /* activation workspace, caller-allocated: see dprb_encoder_workspace_bytes */
+  void* workspace;
+  int64_t workspace_bytes;
+  int32_t save_for_backward; /* 0: forward-only (generate_embeddings path) reuses per-layer buffers */
+} dprb_encoder_batch;
+
+int64_t dprb_encoder_workspace_bytes(const dprb_encoder_weights* w, int nseq, int S, int save_for_backward);
+/* pooled fp32 [nseq, hidden] = last-layer hidden state of token 0 of each sequence. */
+int dprb_encoder_fwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b, float* pooled,
+                     dprb_stream_t stream);
+/* Accumulates parameter gradients into w->grads given dpooled fp32 [nseq, hidden].
+ * Layers [layer_hi-1 .. layer_lo] are processed (layer_lo == 0 also runs the embedding backward), so
+ * the host can interleave gradient all-reduce buckets between calls. */
+int dprb_encoder_bwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b, const float* dpooled,
+                     int layer_lo, int layer_hi, dprb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPRB_H_ */

@@ -1,0 +1,272 @@
+"""Per-kernel parity checks: CUDA path (through the C ABI) vs the CPU oracle on the same seeded inputs.
+
+Each check returns a dict of error figures and raises AssertionError when a stated tolerance is exceeded.
+Used by tests/test_ops_gpu.py (pytest -m gpu) and tools/gpu_diag.py (one subprocess per check).
+
+Tolerances (stated here, per the fp contract of BASELINE.json:north_star / SURVEY.md §8c):
+  * bf16-output kernels: |err| <= 2^-7 * max|ref| + small atol   (one bf16 rounding of the result plus fp32
+    accumulation-order noise; inputs are the identical bf16-rounded values on both sides)
+  * fp32-output kernels (scoring/CE, optimizer, wgrad): rel <= 1e-4 unless noted.
+"""
+import math
+
+import torch
+
+from dpr_scale_b200 import ops
+from oracle import encoder as oenc
+from oracle import task as otask
+
+DEV = "cuda"
+
+
+def _bf(x):
+    return x.to(torch.bfloat16)
+
+
+def _close(name, got, ref, rtol_max, atol=0.0, out=None):
+    got = got.detach().float().cpu()
+    ref = ref.detach().float().cpu()
+    assert got.shape == ref.shape, f"{name}: shape {got.shape} vs {ref.shape}"
+    assert torch.isfinite(got).all(), f"{name}: non-finite values"
+    err = float((got - ref).abs().max())
+    scale = float(ref.abs().max())
+    if out is not None:
+        out[name + "_maxerr"] = err
+        out[name + "_scale"] = scale
+    assert err <= rtol_max * scale + atol, f"{name}: max err {err:.4e} > {rtol_max}*{scale:.4e}+{atol}"
+    return err
+
+
+# ------------------------------------------------------------------ GEMM
+def check_gemm(M, N, K, a_mn=False, b_mn=False, epilogue=ops.EPI_BIAS, splits=1, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    A = _bf(torch.randn(M, K, generator=g))
+    B = _bf(torch.randn(N, K, generator=g) * 0.5)
+    bias = torch.randn(N, generator=g)
+    aux = _bf(torch.randn(M, N, generator=g))
+    ref = A.double() @ B.double().T
+    res = {}
+    Ad = (A.T.contiguous() if a_mn else A).to(DEV)
+    Bd = (B.T.contiguous() if b_mn else B).to(DEV)
+    lda = M if a_mn else K
+    ldb = N if b_mn else K
+    bias_d, aux_d = bias.to(DEV), aux.to(DEV)
+    if epilogue in (ops.EPI_F32_ATOMIC_ADD, ops.EPI_F32_STORE):
+        init = torch.randn(M, N, generator=g)
+        out = init.clone().to(DEV)
+        use_bias = epilogue == ops.EPI_F32_STORE
+        ops.gemm(Ad, Bd, out, M, N, K, lda, ldb, N, a_mn, b_mn, epilogue, bias_d if use_bias else None, splits=splits)
+        want = ref + (init.double() if epilogue == ops.EPI_F32_ATOMIC_ADD else bias.double())
+        _close("gemm_f32", out, want, 2e-5 * math.sqrt(K), 1e-4, res)
+        return res
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    out2 = torch.empty(M, N, dtype=torch.bfloat16, device=DEV) if epilogue == ops.EPI_BIAS_GELU else None
+    use_aux = epilogue in (ops.EPI_BIAS_RESIDUAL, ops.EPI_DGELU)
+    use_bias = epilogue != ops.EPI_DGELU
+    ops.gemm(Ad, Bd, out, M, N, K, lda, ldb, N, a_mn, b_mn, epilogue, bias_d if use_bias else None,
+             aux_d if use_aux else None, N if use_aux else 0, out2)
+    torch.cuda.synchronize()
+    if epilogue == ops.EPI_BIAS:
+        want = ref + bias.double()
+    elif epilogue == ops.EPI_BIAS_RESIDUAL:
+        want = ref + bias.double() + aux.double()
+    elif epilogue == ops.EPI_BIAS_GELU:
+        pre = ref + bias.double()
+        _close("gemm_pre", out2, pre, 2 ** -7, 1e-3, res)
+        want = oenc.gelu_erf(out2.double().cpu())  # forward applies GELU to the stored bf16 pre-activation
+    else:  # DGELU
+        x = aux.double()
+        cdf = 0.5 * (1 + torch.erf(x / math.sqrt(2)))
+        pdf = torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi)
+        want = ref * (cdf + x * pdf)
+    _close("gemm_out", out, want, 2 ** -7, 1e-3, res)
+    return res
+
+
+# ------------------------------------------------------------------ LayerNorm / embeddings
+def check_ln(T=777, H=768, cls_stride=0, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    z = _bf(torch.randn(T, H, generator=g) * 2 + 0.3)
+    gamma = 1 + 0.1 * torch.randn(H, generator=g)
+    beta = 0.1 * torch.randn(H, generator=g)
+    eps = 1e-12
+    res = {}
+    y, stats, cls = ops.ln_fwd(z.to(DEV), gamma.to(DEV), beta.to(DEV), eps, cls_stride)
+    zr = z.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = oenc.layer_norm(zr, gr, br, eps)
+    _close("ln_y", y, yr, 2 ** -7, 1e-3, res)
+    if cls_stride:
+        _close("ln_cls", cls, yr[::cls_stride], 1e-5, 1e-5, res)
+    # backward
+    dy = _bf(torch.randn(T, H, generator=g))
+    dgamma = torch.zeros(H, device=DEV)
+    dbeta = torch.zeros(H, device=DEV)
+    dbias = torch.zeros(H, device=DEV)
+    if cls_stride:
+        ncls = (T + cls_stride - 1) // cls_stride
+        dy_cls = torch.randn(ncls, H, generator=g)
+        dyr = torch.zeros(T, H)
+        dyr[::cls_stride] = dy_cls
+        dz = ops.ln_bwd(None, z.to(DEV), stats, gamma.to(DEV), dgamma, dbeta, dbias, dy_cls.to(DEV), cls_stride)
+    else:
+        dyr = dy.float()
+        dz = ops.ln_bwd(dy.to(DEV), z.to(DEV), stats, gamma.to(DEV), dgamma, dbeta, dbias)
+    yr.backward(dyr)
+    _close("ln_dz", dz, zr.grad, 2 ** -7, 1e-3, res)
+    _close("ln_dgamma", dgamma, gr.grad, 1e-4, 1e-3, res)
+    _close("ln_dbeta", dbeta, br.grad, 1e-4, 1e-3, res)
+    _close("ln_dbias", dbias, dz.float().cpu().sum(0), 1e-4, 1e-3, res)
+    return res
+
+
+def check_embed(T=500, H=768, vocab=1000, max_pos=64, type_vocab=2, seed=2):
+    g = torch.Generator().manual_seed(seed)
+    word = torch.randn(vocab, H, generator=g) * 0.5
+    pos = torch.randn(max_pos, H, generator=g) * 0.5
+    typ = torch.randn(type_vocab, H, generator=g) * 0.5
+    gamma = 1 + 0.1 * torch.randn(H, generator=g)
+    beta = 0.1 * torch.randn(H, generator=g)
+    ids = torch.randint(0, vocab, (T,), generator=g)
+    ids[:50] = 7  # repeated ids -> atomic accumulation
+    tts = torch.randint(0, type_vocab, (T,), generator=g)
+    pids = torch.arange(T) % max_pos
+    eps = 1e-12
+    res = {}
+    d = lambda t: t.to(DEV)
+    y, stats = ops.embed_ln_fwd(d(ids), d(tts), d(pids), d(word), d(pos), d(typ), d(gamma), d(beta), eps)
+    wr, pr, tr = (t.clone().requires_grad_(True) for t in (word, pos, typ))
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = oenc.layer_norm((wr[ids] + tr[tts]) + pr[pids], gr, br, eps)
+    _close("emb_y", y, yr, 2 ** -7, 1e-3, res)
+    dy = _bf(torch.randn(T, H, generator=g))
+    dword, dpos, dtyp = torch.zeros_like(d(word)), torch.zeros_like(d(pos)), torch.zeros_like(d(typ))
+    dgamma, dbeta = torch.zeros(H, device=DEV), torch.zeros(H, device=DEV)
+    ops.embed_ln_bwd(d(dy), d(ids), d(tts), d(pids), d(word), d(pos), d(typ), d(gamma), stats, dword, dpos, dtyp, dgamma, dbeta)
+    yr.backward(dy.float())
+    _close("emb_dword", dword, wr.grad, 1e-4, 1e-3, res)
+    _close("emb_dpos", dpos, pr.grad, 1e-4, 1e-3, res)
+    _close("emb_dtype", dtyp, tr.grad, 1e-4, 1e-3, res)
+    _close("emb_dgamma", dgamma, gr.grad, 1e-4, 1e-3, res)
+    _close("emb_dbeta", dbeta, br.grad, 1e-4, 1e-3, res)
+    return res
+
+
+def check_colsum(T=1000, N=2304, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    x = _bf(torch.randn(T, N, generator=g))
+    out = torch.ones(N, device=DEV)
+    ops.colsum(x.to(DEV), out)
+    res = {}
+    _close("colsum", out, 1 + x.double().sum(0), 1e-5, 1e-3, res)
+    return res
+
+
+# ------------------------------------------------------------------ attention
+def check_attention(nseq=3, S=128, heads=2, masked=True, seed=4):
+    g = torch.Generator().manual_seed(seed)
+    H = heads * 64
+    T = nseq * S
+    qkv = _bf(torch.randn(T, 3 * H, generator=g))
+    am = torch.ones(nseq, S, dtype=torch.int32)
+    if masked:
+        for i in range(nseq):
+            ln = int(torch.randint(max(1, S // 4), S + 1, (1,), generator=g))
+            am[i, ln:] = 0
+    res = {}
+    ctx, lse = ops.attn_fwd(qkv.to(DEV), am.to(DEV) if masked else None, nseq, S, heads)
+    qr = qkv.float().requires_grad_(True)
+    x = qr.view(nseq, S, 3, heads, 64)
+    q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))  # nseq, heads, S, 64
+    sc = q @ k.transpose(-1, -2) / 8.0
+    if masked:
+        sc = sc.masked_fill(am.view(nseq, 1, 1, S) == 0, float("-inf"))
+    p = torch.softmax(sc, -1)
+    cr = (p @ v).transpose(1, 2).reshape(T, H)
+    _close("attn_ctx", ctx, cr, 2 ** -7, 2e-3, res)
+    _close("attn_lse", lse, torch.logsumexp(sc, -1), 1e-4, 1e-3, res)
+    dctx = _bf(torch.randn(T, H, generator=g))
+    dqkv = ops.attn_bwd(qkv.to(DEV), am.to(DEV) if masked else None, ctx, lse, dctx.to(DEV), nseq, S, heads)
+    cr.backward(dctx.float())
+    # P and dS are rounded to bf16 before the second matmuls (as in any flash-style kernel): 2^-6 headroom
+    _close("attn_dqkv", dqkv, qr.grad, 2 ** -6, 4e-3, res)
+    return res
+
+
+# ------------------------------------------------------------------ scoring + CE
+def check_score_ce(Q=37, C=250, d=768, inv_t=2.0, q0=8, nq=16, c0=40, nc=100, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randn(Q, d, generator=g)
+    c = torch.randn(C, d, generator=g)
+    mask = torch.rand(C, generator=g) < 0.1
+    labels = torch.randint(0, C, (Q,), generator=g)
+    mask[labels] = False
+    res = {}
+    d_ = lambda t: t.to(DEV)
+    loss_sum, lse, logits = ops.score_ce_fwd(d_(q), d_(c), d_(mask.to(torch.uint8)), d_(labels), inv_t)
+    qr, cr = q.clone().requires_grad_(True), c.clone().requires_grad_(True)
+    loss_r, logits_r = otask.in_batch_loss(qr, cr, mask, labels, 1.0 / inv_t)
+    fin = torch.isfinite(logits_r)
+    assert torch.equal(torch.isfinite(logits.cpu()), fin)
+    _close("score_logits", torch.where(fin, logits.cpu(), torch.zeros(())), torch.where(fin, logits_r, torch.zeros(())), 1e-5, 1e-3, res)
+    _close("score_lse", lse, torch.logsumexp(logits_r, 1), 1e-5, 1e-3, res)
+    got_loss = float(loss_sum) / Q
+    res["loss_abs_err"] = abs(got_loss - float(loss_r))
+    assert res["loss_abs_err"] <= 1e-4 * max(1.0, abs(float(loss_r))), res
+    dq, dc = ops.score_ce_bwd(d_(q), d_(c), logits, d_(labels), lse, 1.0, inv_t, q0, nq, c0, nc)
+    loss_r.backward()
+    _close("score_dq", dq, qr.grad[q0:q0 + nq], 1e-4, 1e-6, res)
+    _close("score_dc", dc, cr.grad[c0:c0 + nc], 1e-4, 1e-6, res)
+    return res
+
+
+# ------------------------------------------------------------------ optimizer
+def check_adamw(n=100003, seed=6):
+    g = torch.Generator().manual_seed(seed)
+    p = torch.randn(n + 1, generator=g)[:n].clone()
+    res = {}
+    pd, md, vd = p.to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    shadow = torch.empty(n, dtype=torch.bfloat16, device=DEV)
+    pr, mr, vr = p.clone(), torch.zeros(n), torch.zeros(n)
+    for step in range(1, 4):
+        gr = torch.randn(n, generator=g) * 3
+        gd = gr.to(DEV)
+        ss = torch.zeros(1, device=DEV)
+        ops.sumsq(gd, ss)
+        ops.adamw_step(pd, gd, md, vd, shadow, 1e-3, 0.9, 0.999, 1e-8, 0.01, step, 0.5, ss, 2.0)
+        coef, total = otask.clip_coef([gr * 0.5], 2.0)
+        res["norm_rel_err"] = abs(math.sqrt(float(ss)) * 0.5 - total) / total
+        assert res["norm_rel_err"] < 1e-4
+        otask.adamw_step(pr, gr * 0.5 * coef, mr, vr, step, 1e-3, weight_decay=0.01)
+    _close("adam_p", pd, pr, 1e-5, 1e-6, res)
+    _close("adam_m", md, mr, 1e-4, 1e-7, res)
+    _close("adam_v", vd, vr, 1e-4, 1e-9, res)
+    _close("adam_shadow", shadow, pr, 2 ** -8, 1e-6, res)
+    return res
+
+
+CHECKS = {
+    "gemm_kk_bias_irregular": lambda: check_gemm(300, 520, 200),
+    "gemm_kk_bias_big": lambda: check_gemm(1024, 768, 768),
+    "gemm_kk_gelu": lambda: check_gemm(512, 1024, 256, epilogue=ops.EPI_BIAS_GELU),
+    "gemm_kk_residual": lambda: check_gemm(384, 768, 512, epilogue=ops.EPI_BIAS_RESIDUAL),
+    "gemm_kmn_dgelu": lambda: check_gemm(384, 512, 256, b_mn=True, epilogue=ops.EPI_DGELU),
+    "gemm_kmn_bias": lambda: check_gemm(300, 520, 200, b_mn=True),
+    "gemm_mnk_bias": lambda: check_gemm(256, 512, 320, a_mn=True),
+    "gemm_mnmn_atomic_split": lambda: check_gemm(768, 768, 4096, a_mn=True, b_mn=True, epilogue=ops.EPI_F32_ATOMIC_ADD, splits=0),
+    "gemm_mnmn_atomic_irregular": lambda: check_gemm(200, 264, 1000, a_mn=True, b_mn=True, epilogue=ops.EPI_F32_ATOMIC_ADD, splits=3),
+    "gemm_kk_f32_store": lambda: check_gemm(130, 260, 96, epilogue=ops.EPI_F32_STORE),
+    "gemm_many_tiles": lambda: check_gemm(4096, 2304, 768),
+    "ln_768": lambda: check_ln(777, 768),
+    "ln_1024_cls": lambda: check_ln(512, 1024, cls_stride=64),
+    "ln_128": lambda: check_ln(100, 128),
+    "embed": lambda: check_embed(),
+    "colsum": lambda: check_colsum(),
+    "attn_128_masked": lambda: check_attention(3, 128, 2, True),
+    "attn_64_nomask": lambda: check_attention(2, 64, 3, False),
+    "attn_100_masked": lambda: check_attention(2, 100, 2, True),
+    "attn_256_masked": lambda: check_attention(2, 256, 1, True),
+    "score_ce": lambda: check_score_ce(),
+    "score_ce_small": lambda: check_score_ce(Q=8, C=16, d=128, inv_t=1.0, q0=0, nq=8, c0=0, nc=16),
+    "adamw": lambda: check_adamw(),
+}

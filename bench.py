@@ -1,0 +1,359 @@
+#!/usr/bin/env python3
+"""bench.py — query+ctx pairs/sec of the bi-encoder contrastive training step (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path (one rank per GPU)
+  python bench.py --impl reference ...                      # the reference's own CPU path (HF + torch, fp32)
+  python bench.py --impl stock ...                          # stock HF + PyTorch on the same GPU (the 1.5x denominator)
+
+A "step" = zero_grad -> both encoders fwd -> (all-gather) -> fused scoring+CE -> backward -> (grad all-reduce)
+-> clip(2.0) + AdamW + LambdaLR, on one synthetic batch of configs[1]/[2]: BERT-base, S=128, 128 queries/GPU,
+1 pos + 7 hard negatives (1024 contexts/GPU), in-batch (global when N>1) negatives.  Prints ONE JSON line.
+"""
+import argparse
+import ctypes
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+BERT_BASE = dict(model_type="bert", vocab_size=30522, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
+                 intermediate_size=3072, max_position_embeddings=512, type_vocab_size=2, layer_norm_eps=1e-12,
+                 pad_token_id=0, initializer_range=0.02)
+WORKLOADS = {
+    # name: (model cfg, queries/GPU, hard negs, seq len)
+    "bert-base_s128_b128_n7": (BERT_BASE, 128, 7, 128),
+    "bert-base_s64_b8_n1": (BERT_BASE, 8, 1, 64),
+}
+
+
+def flops_per_token_train(cfg, S):
+    H, I, L = cfg["hidden_size"], cfg["intermediate_size"], cfg["num_hidden_layers"]
+    return 3 * L * (2 * (4 * H * H + 2 * H * I) + 4 * S * H)
+
+
+def synth_batch(rank, cfg, B, n, S, pin=True):
+    """BASELINE.md §5 variant A: all sequences exactly S tokens, mask all ones."""
+    g = torch.Generator().manual_seed(1234 + rank)
+    C = B * (1 + n)
+
+    def toks(N):
+        ids = torch.randint(1000, 30000, (N, S), generator=g)
+        ids[:, 0] = 101
+        ids[:, -1] = 102
+        d = {"input_ids": ids, "token_type_ids": torch.zeros_like(ids), "attention_mask": torch.ones_like(ids)}
+        return {k: (v.pin_memory() if pin else v) for k, v in d.items()}
+
+    b = {"query_ids": toks(B), "contexts_ids": toks(C), "pos_ctx_indices": torch.arange(B) * (1 + n),
+         "ctx_mask": torch.zeros(C, dtype=torch.bool)}
+    if pin:
+        b["pos_ctx_indices"] = b["pos_ctx_indices"].pin_memory()
+        b["ctx_mask"] = b["ctx_mask"].pin_memory()
+    return b
+
+
+def to_device(batch, dev):
+    out = {}
+    for k, v in batch.items():
+        out[k] = {kk: vv.to(dev, non_blocking=True) for kk, vv in v.items()} if isinstance(v, dict) else v.to(dev, non_blocking=True)
+    return out
+
+
+def batch_bytes(batch):
+    n = 0
+    for v in batch.values():
+        for t in (v.values() if isinstance(v, dict) else [v]):
+            n += t.numel() * t.element_size()
+    return n
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for nm, val in zip(names, r[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json, sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------- CPU reference path
+def cpu_reference_step_factory(cfg, pairs, n, S, threads):
+    """The reference's own CPU path: HF BertModel x2 (fp32) + reference scoring/CE + clip + torch AdamW."""
+    from oracle import hf_path, task as otask
+    torch.set_num_threads(threads)
+    hf_cfg = hf_path.make_config("bert", **{k: v for k, v in cfg.items() if k not in ("model_type",)})
+    torch.manual_seed(0)
+    qe, ce = hf_path.CLSEncoder(hf_cfg, dropout=0.1), hf_path.CLSEncoder(hf_cfg, dropout=0.1)
+    params = [p for p in list(qe.parameters()) + list(ce.parameters())]
+    opt = torch.optim.AdamW(params, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
+    batch = synth_batch(0, cfg, pairs, n, S, pin=False)
+
+    def step():
+        opt.zero_grad()
+        q, c = qe(batch["query_ids"]), ce(batch["contexts_ids"])
+        loss, _ = otask.in_batch_loss(q, c, batch["ctx_mask"], batch["pos_ctx_indices"], 1.0)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([p for p in params if p.grad is not None], 2.0)
+        opt.step()
+        return float(loss)
+    return step
+
+
+def time_cpu_reference(cfg, pairs, n, S, steps, warmup, threads):
+    step = cpu_reference_step_factory(cfg, pairs, n, S, threads)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return pairs * steps / dt, dt / steps
+
+
+# --------------------------------------------------------------------------------------- main arms
+def run_reference(args, workload):
+    cfg, B, n, S = WORKLOADS[workload]
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    pairs = args.ref_pairs  # bounded sample of the same workload: `pairs` queries with 1+n contexts each, S tokens
+    steps, warmup = args.steps, args.warmup
+    value, spstep = time_cpu_reference(cfg, pairs, n, S, steps, warmup, threads)
+    line = {
+        "impl": "reference", "metric": "query+ctx pairs/sec (BERT-base, seq128)", "value": value, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": spstep * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "sample_pairs_per_step": pairs, "hard_negatives": n, "seq_len": S,
+                   "dropout": 0.1, "optimizer": "torch.optim.AdamW + clip 2.0"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
+                         "sample": f"{pairs} pairs/step x {steps} steps of {workload} (HF BertModel x2 fp32, fwd+bwd+AdamW)"},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_stock(args, workload):
+    """Stock HF + PyTorch on the GPU: reference precision:16 analogue (bf16 autocast), torch AdamW, clip 2.0."""
+    from oracle import hf_path, task as otask
+    cfg, B, n, S = WORKLOADS[workload]
+    dev = torch.device("cuda", 0)
+    hf_cfg = hf_path.make_config("bert", **{k: v for k, v in cfg.items() if k not in ("model_type",)})
+    torch.manual_seed(0)
+    qe, ce = hf_path.CLSEncoder(hf_cfg, dropout=args.dropout).to(dev), hf_path.CLSEncoder(hf_cfg, dropout=args.dropout).to(dev)
+    params = list(qe.parameters()) + list(ce.parameters())
+    opt = torch.optim.AdamW(params, lr=1e-5, fused=True)
+    batch = to_device(synth_batch(0, cfg, B, n, S), dev)
+    amp = torch.bfloat16 if args.stock_dtype == "bf16" else torch.float16
+    scaler = torch.amp.GradScaler("cuda", enabled=(amp == torch.float16))
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=amp):
+            q, c = qe(batch["query_ids"]), ce(batch["contexts_ids"])
+            loss, _ = otask.in_batch_loss(q, c, batch["ctx_mask"], batch["pos_ctx_indices"], 1.0)
+        scaler.scale(loss).backward()
+        scaler.unscale_(opt)
+        torch.nn.utils.clip_grad_norm_([p for p in params if p.grad is not None], 2.0)
+        scaler.step(opt)
+        scaler.update()
+        return loss
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    print(json.dumps({"impl": "stock", "metric": "query+ctx pairs/sec (BERT-base, seq128)", "value": B / (ms / 1e3),
+                      "unit": "pairs/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                      "dtype": args.stock_dtype, "data": "synthetic", "higher_is_better": True,
+                      "config": {"workload": workload, "dropout": args.dropout, "attn": "sdpa",
+                                 "optimizer": "torch.optim.AdamW(fused) + clip 2.0"},
+                      "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
+
+
+def run_b200(args, workload):
+    from dpr_scale_b200 import _lib, ops
+    from dpr_scale_b200.task.dpr_task import DenseRetrieverTask
+    from dpr_scale_b200.trainer import Trainer
+
+    cfg, B, n, S = WORKLOADS[workload]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    task = DenseRetrieverTask(
+        transform={}, datamodule=None, shared_model=False, in_batch_negatives=True, warmup_steps=10,
+        model={"_target_": "dpr_scale_b200.models.hf_model.HFEncoder.from_config", "config": cfg, "dropout": 0.0},
+        optim={"_target_": "dpr_scale_b200.optim.FusedAdamW", "lr": 1e-5, "betas": [0.9, 0.999], "eps": 1e-8,
+               "weight_decay": 0.0})
+    trainer = Trainer(max_steps=10 ** 6, gradient_clip_val=2.0, device=dev)
+    trainer.attach(task, None, "fit")
+    task.train()
+    host_batch = synth_batch(rank, cfg, B, n, S)
+    dev_batch = to_device(host_batch, dev)
+    lib = _lib.load()
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    # ---- kernel-path number: inputs resident in HBM
+    for i in range(args.warmup):
+        trainer.training_step(dev_batch, i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.LAUNCHES
+    _lib.check(lib.dprb_gemm_profile_enable(1, 400 * args.steps + 64), "profile_enable")
+    ms_step = timed(lambda i: trainer.training_step(dev_batch, i), args.steps)
+    launches = (ops.LAUNCHES - launches0)
+    tms, tfl, nl = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+    _lib.check(lib.dprb_gemm_profile_read(ctypes.byref(tms), ctypes.byref(tfl), ctypes.byref(nl)), "profile_read")
+    _lib.check(lib.dprb_gemm_profile_enable(0, 0), "profile_disable")
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end number: host (pinned) inputs -> H2D each step, loss read back each step
+    losses = []
+
+    def e2e_step(i):
+        b = to_device(host_batch, dev)
+        losses.append(float(trainer.training_step(b, i)))  # D2H read of the step's loss
+
+    e2e_step(0)
+    ms_e2e = timed(e2e_step, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pairs_step = B * world
+    value = pairs_step / (ms_step / 1e3)
+    peak_tf, peak_hbm, peak_src = peaks()
+    gemm_tflops = (tfl.value / 1e12) / (tms.value / 1e3) if tms.value > 0 else 0.0
+    tokens = B * (2 + n) * S
+    step_flops = tokens * flops_per_token_train(cfg, S)
+    line = {
+        "metric": "query+ctx pairs/sec (BERT-base, seq128)", "value": value, "unit": "pairs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload, "model": "BERT-base x2 (query+context, shared_model=false)",
+                   "queries_per_gpu": B, "hard_negatives": n, "contexts_per_gpu": B * (1 + n), "seq_len": S,
+                   "global_batch": pairs_step, "parallelism": f"dp{world}", "negatives": "global in-batch" if world > 1 else "in-batch",
+                   "optimizer": "fused AdamW + clip 2.0 + LambdaLR", "dropout": 0.0,
+                   "l2": "working set (>=40 GB activations + 0.9 GB weights/step) exceeds the 126 MB L2; no flush needed"},
+        "e2e": {"value": pairs_step / (ms_e2e / 1e3), "unit": "pairs/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": batch_bytes(host_batch), "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05 UMMA 128x256x16)",
+                     "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tflops / peak_tf,
+                     "peak_source": peak_src, "traffic": None, "gemm_launches": nl.value,
+                     "gemm_ms_per_step": tms.value / args.steps, "gemm_share_of_step": (tms.value / args.steps) / ms_step,
+                     "step_model_tflops": step_flops / (ms_step / 1e3) / 1e12,
+                     "step_frac_of_peak": step_flops / (ms_step / 1e3) / 1e12 / peak_tf},
+        "loss_first_last": [losses[0], losses[-1]] if losses else None,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, sp = time_cpu_reference(cfg, args.ref_pairs, n, S, 2, 1, threads)
+        line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
+                                "sample": f"{args.ref_pairs} pairs/step x 2 steps (+1 warm-up) of {workload}: HF BertModel x2 fp32 "
+                                          f"fwd+bwd+clip+AdamW on {threads} host threads"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "stock"])
+    ap.add_argument("--workload", default="bert-base_s128_b128_n7", choices=sorted(WORKLOADS))
+    ap.add_argument("--ref-pairs", type=int, default=2, help="pairs per step of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dropout", type=float, default=0.0, help="stock arm only")
+    ap.add_argument("--stock-dtype", default="bf16", choices=["bf16", "fp16"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args, args.workload)
+    if args.impl == "stock":
+        return run_stock(args, args.workload)
+    return run_b200(args, args.workload)
+
+
+if __name__ == "__main__":
+    main()

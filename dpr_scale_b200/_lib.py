@@ -49,6 +49,8 @@ SIGNATURES = {
     "dprb_num_sms": (c_int, []),
     "dprb_gemm_bf16": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_int, c_int,
                                _P, _P, c_int64, _P, c_float, c_int, _P]),
+    "dprb_gemm_profile_enable": (c_int, [c_int, c_int]),
+    "dprb_gemm_profile_read": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int64)]),
     "dprb_embed_ln_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
                                   c_float, _P]),
     "dprb_embed_ln_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
@@ -57,7 +59,7 @@ SIGNATURES = {
     "dprb_colsum_bf16": (c_int, [_P, c_int64, _P, c_int, c_int, _P]),
     "dprb_attn_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "dprb_attn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
-    "dprb_score_ce_fwd": (c_int, [_P, _P, _P, _P, c_float, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "dprb_score_ce_fwd": (c_int, [_P, _P, _P, _P, _P, c_float, _P, _P, _P, c_int, c_int, c_int, _P]),
     "dprb_score_ce_bwd": (c_int, [_P, _P, _P, _P, _P, c_float, c_float, _P, _P, c_int, c_int, c_int, c_int,
                                   c_int, c_int, c_int, _P]),
     "dprb_sumsq_f32": (c_int, [_P, c_int64, _P, _P]),

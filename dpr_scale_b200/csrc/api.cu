@@ -45,6 +45,14 @@ int dprb_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, i
                    alpha, splits, S(stream));
 }
 
+int dprb_gemm_profile_enable(int enable, int max_launches) { return gemm_profile_enable(enable, max_launches); }
+int dprb_gemm_profile_read(double* total_ms, double* total_flops, int64_t* launches) {
+  long long n = 0;
+  int rc = gemm_profile_read(total_ms, total_flops, &n);
+  if (launches) *launches = n;
+  return rc;
+}
+
 int dprb_embed_ln_fwd(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, const float* word,
                       const float* pos, const float* type, const float* gamma, const float* beta, void* y,
                       float* stats, int T, int H, int vocab, int max_pos, int type_vocab, float eps,
@@ -79,10 +87,10 @@ int dprb_attn_bwd(const void* qkv, const int32_t* attn_mask, const void* ctx, co
                   void* dqkv, int nseq, int Sq, int heads, dprb_stream_t stream) {
   return attn_bwd_lse(qkv, attn_mask, ctx, lse, dctx, dqkv, nseq, Sq, heads, S(stream));
 }
-int dprb_score_ce_fwd(const float* q, const float* c, const uint8_t* col_mask, const int64_t* labels,
-                      float inv_temperature, float* lse, float* loss_sum, float* logits, int Q, int C, int d,
-                      dprb_stream_t stream) {
-  return score_ce_fwd(q, c, col_mask, labels, inv_temperature, lse, loss_sum, logits, Q, C, d, S(stream));
+int dprb_score_ce_fwd(const float* q, const float* c, const uint8_t* col_mask, const uint8_t* pair_mask,
+                      const int64_t* labels, float inv_temperature, float* lse, float* loss_sum, float* logits,
+                      int Q, int C, int d, dprb_stream_t stream) {
+  return score_ce_fwd(q, c, col_mask, pair_mask, labels, inv_temperature, lse, loss_sum, logits, Q, C, d, S(stream));
 }
 int dprb_score_ce_bwd(const float* q, const float* c, const float* logits, const int64_t* labels,
                       const float* lse, float grad_scale, float inv_temperature, float* dq, float* dc, int Q,

@@ -9,6 +9,9 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long l
               long long ldd, int a_mn_major, int b_mn_major, int epilogue, const float* bias, const void* aux,
               long long ld_aux, void* out2, float alpha, int splits, cudaStream_t stream);
 
+int gemm_profile_enable(int enable, int max_launches);
+int gemm_profile_read(double* total_ms, double* total_flops, long long* launches);
+
 int embed_ln_fwd(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, const float* word,
                  const float* pos, const float* type, const float* gamma, const float* beta, void* y, float* stats,
                  int T, int H, int vocab, int max_pos, int type_vocab, float eps, cudaStream_t stream);
@@ -28,8 +31,9 @@ int attn_fwd_lse(const void* qkv, const int32_t* attn_mask, void* ctx, float* ls
 int attn_bwd_lse(const void* qkv, const int32_t* attn_mask, const void* ctx, const float* lse, const void* dctx,
                  void* dqkv, int nseq, int S, int heads, cudaStream_t stream);
 
-int score_ce_fwd(const float* q, const float* c, const uint8_t* col_mask, const int64_t* labels, float inv_t,
-                 float* lse, float* loss_sum, float* logits, int Q, int C, int d, cudaStream_t stream);
+int score_ce_fwd(const float* q, const float* c, const uint8_t* col_mask, const uint8_t* pair_mask,
+                 const int64_t* labels, float inv_t, float* lse, float* loss_sum, float* logits, int Q, int C, int d,
+                 cudaStream_t stream);
 int score_ce_bwd(const float* q, const float* c, const float* logits, const int64_t* labels, const float* lse,
                  float grad_scale, float inv_t, float* dq, float* dc, int Q, int C, int d, int q0, int nq, int c0,
                  int nc, cudaStream_t stream);

@@ -10,6 +10,7 @@
 // D[M,N] = epi( sum_k A(m,k) * B(n,k) ).  Each operand may be K-major (row = MN index, K contiguous)
 // or MN-major (row = K index, MN contiguous); the latter lets dgrad read W[N_out,K_in] and wgrad
 // read dY[T,N_out] / X[T,K_in] in place, with no transposed copies.
+#include <vector>
 #include "common.cuh"
 #include "dprb_internal.h"
 
@@ -327,6 +328,15 @@ int make_tmap(CUtensorMap* out, const void* base, long long rows, long long cols
   return 0;
 }
 
+// ---- optional live profiling: CUDA events around every GEMM launch (bench.py's roofline leg) ----
+struct GemmProfile {
+  bool enabled = false;
+  std::vector<cudaEvent_t> ev;   // pairs
+  std::vector<double> flops;
+  size_t used = 0;
+};
+GemmProfile g_prof;
+
 int choose_splits(int tiles, int k_blocks, int sms) {
   // minimise the makespan ceil(tiles*s/sms)/s over s, keeping >= 4 k-blocks per split
   int best = 1;
@@ -388,14 +398,52 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long l
       DPRB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
       attr_set = true;
     }
+    const bool prof = g_prof.enabled && g_prof.used + 2 <= g_prof.ev.size();
+    if (prof) DPRB_CHECK_CUDA(cudaEventRecord(g_prof.ev[g_prof.used], stream));
     kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
     DPRB_CHECK_CUDA(cudaGetLastError());
+    if (prof) {
+      DPRB_CHECK_CUDA(cudaEventRecord(g_prof.ev[g_prof.used + 1], stream));
+      g_prof.flops.push_back(2.0 * (double)M * (double)N * (double)K);
+      g_prof.used += 2;
+    }
     return 0;
   };
   if (!a_mn_major && !b_mn_major) return launch(gemm_bf16_kernel<0, 0>);
   if (!a_mn_major && b_mn_major) return launch(gemm_bf16_kernel<0, 1>);
   if (a_mn_major && !b_mn_major) return launch(gemm_bf16_kernel<1, 0>);
   return launch(gemm_bf16_kernel<1, 1>);
+}
+
+int gemm_profile_enable(int enable, int max_launches) {
+  if (enable) {
+    const size_t want = (size_t)max_launches * 2;
+    while (g_prof.ev.size() < want) {
+      cudaEvent_t e;
+      DPRB_CHECK_CUDA(cudaEventCreate(&e));
+      g_prof.ev.push_back(e);
+    }
+    g_prof.used = 0;
+    g_prof.flops.clear();
+  }
+  g_prof.enabled = enable != 0;
+  return 0;
+}
+
+// Sums the recorded launch durations (synchronises on each end event). Outputs: total ms, total FLOPs, launches.
+int gemm_profile_read(double* total_ms, double* total_flops, long long* launches) {
+  double ms = 0.0, fl = 0.0;
+  for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
+    DPRB_CHECK_CUDA(cudaEventSynchronize(g_prof.ev[i + 1]));
+    float t = 0.f;
+    DPRB_CHECK_CUDA(cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]));
+    ms += t;
+    fl += g_prof.flops[i / 2];
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  if (launches) *launches = (long long)(g_prof.used / 2);
+  return 0;
 }
 
 }  // namespace dprb

@@ -20,7 +20,7 @@ constexpr int FWD_WARPS = 8;
 
 __global__ void __launch_bounds__(FWD_WARPS * 32)
 score_ce_fwd_kernel(const float* __restrict__ q, const float* __restrict__ c, const uint8_t* __restrict__ col_mask,
-                    const int64_t* __restrict__ labels, float inv_t, float* __restrict__ lse_out,
+                    const uint8_t* __restrict__ pair_mask, const int64_t* __restrict__ labels, float inv_t, float* __restrict__ lse_out,
                     float* __restrict__ loss_sum, float* __restrict__ logits, int Q, int C, int d) {
   extern __shared__ float sm[];
   float* qs = sm;                       // [QB][d]
@@ -68,7 +68,8 @@ score_ce_fwd_kernel(const float* __restrict__ q, const float* __restrict__ c, co
         const bool masked = col_mask != nullptr && col_mask[col] != 0;
 #pragma unroll
         for (int r = 0; r < QB; ++r) {
-          const float s = masked ? -INFINITY : acc[r][j] * inv_t;
+          const bool pm = pair_mask != nullptr && row0 + r < Q && pair_mask[(long long)(row0 + r) * C + col] != 0;
+          const float s = (masked || pm) ? -INFINITY : acc[r][j] * inv_t;
           if (logits != nullptr && lane == ((r * CW + j) & 31) && row0 + r < Q)
             logits[(long long)(row0 + r) * C + col] = s;
           if (s > m[r]) { l[r] = l[r] * __expf(m[r] - s) + 1.f; m[r] = s; }
@@ -165,8 +166,9 @@ score_ce_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ 
 
 }  // namespace
 
-int score_ce_fwd(const float* q, const float* c, const uint8_t* col_mask, const int64_t* labels, float inv_t,
-                 float* lse, float* loss_sum, float* logits, int Q, int C, int d, cudaStream_t stream) {
+int score_ce_fwd(const float* q, const float* c, const uint8_t* col_mask, const uint8_t* pair_mask,
+                 const int64_t* labels, float inv_t, float* lse, float* loss_sum, float* logits, int Q, int C, int d,
+                 cudaStream_t stream) {
   DPRB_REQUIRE(Q >= 0 && C > 0 && d > 0, "score_ce_fwd: bad shape Q=%d C=%d d=%d", Q, C, d);
   DPRB_REQUIRE(lse != nullptr, "score_ce_fwd: lse output required");
   if (Q == 0) return 0;
@@ -177,7 +179,7 @@ int score_ce_fwd(const float* q, const float* c, const uint8_t* col_mask, const 
     DPRB_CHECK_CUDA(cudaFuncSetAttribute(score_ce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
-  score_ce_fwd_kernel<<<(Q + QB - 1) / QB, FWD_WARPS * 32, smem, stream>>>(q, c, col_mask, labels, inv_t, lse,
+  score_ce_fwd_kernel<<<(Q + QB - 1) / QB, FWD_WARPS * 32, smem, stream>>>(q, c, col_mask, pair_mask, labels, inv_t, lse,
                                                                            loss_sum, logits, Q, C, d);
   DPRB_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -117,13 +117,13 @@ def attn_bwd(qkv, attn_mask, ctx, lse, dctx, nseq, S, heads):
     return dqkv
 
 
-def score_ce_fwd(q, c, col_mask, labels, inv_temperature, want_logits=True):
+def score_ce_fwd(q, c, col_mask, labels, inv_temperature, want_logits=True, pair_mask=None):
     Q, d = q.shape
     C = c.shape[0]
     lse = torch.empty(Q, dtype=torch.float32, device=q.device)
     loss_sum = torch.zeros(1, dtype=torch.float32, device=q.device)
     logits = torch.empty(Q, C, dtype=torch.float32, device=q.device) if want_logits else None
-    check(_lib.load().dprb_score_ce_fwd(_ptr(q), _ptr(c), _ptr(col_mask), _ptr(labels), float(inv_temperature),
+    check(_lib.load().dprb_score_ce_fwd(_ptr(q), _ptr(c), _ptr(col_mask), _ptr(pair_mask), _ptr(labels), float(inv_temperature),
                                         _ptr(lse), _ptr(loss_sum), _ptr(logits), Q, C, d, _stream()),
           "dprb_score_ce_fwd")
     _count()

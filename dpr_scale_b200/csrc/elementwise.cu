@@ -20,6 +20,10 @@ __device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
   float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
 }
+__device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
+  float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
 __device__ __forceinline__ void load8f(const float* p, float (&v)[8]) {
   float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -167,8 +171,36 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ dy_cls, int
 #pragma unroll
     for (int j = 0; j < 8; ++j) { ag[i][j] = 0.f; ab[i][j] = 0.f; az[i][j] = 0.f; az1[i][j] = 0.f; }
   }
+  // Software prefetch: the packed (bf16) dy / z chunks of the NEXT row are requested before the current row is
+  // reduced, doubling the bytes in flight per warp (the kernel is latency-bound at 1 CTA/SM otherwise).
+  const bool sparse_dy = (dy_cls != nullptr);
+  const bool dense_path = !EMBED && !sparse_dy;
+  uint4 nz[MAXC], ndy[MAXC];
+  if (dense_path && warp_global < T) {
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i)
+      if (act[i]) {
+        const long long o = (long long)warp_global * H + (lane + 32 * i) * 8;
+        nz[i] = ldg_nc_v4(z + o);
+        ndy[i] = ldg_nc_v4(dy + o);
+      }
+  }
   for (int row = warp_global; row < T; row += nwarps) {
-    const bool sparse_dy = (dy_cls != nullptr);
+    uint4 cz[MAXC], cdy[MAXC];
+    if (dense_path) {
+#pragma unroll
+      for (int i = 0; i < MAXC; ++i) { cz[i] = nz[i]; cdy[i] = ndy[i]; }
+      const int nrow = row + nwarps;
+      if (nrow < T) {
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i)
+          if (act[i]) {
+            const long long o = (long long)nrow * H + (lane + 32 * i) * 8;
+            nz[i] = ldg_nc_v4(z + o);
+            ndy[i] = ldg_nc_v4(dy + o);
+          }
+      }
+    }
     if (sparse_dy && (row % cls_stride != 0)) {
       // upstream gradient is identically zero for this row
       if (dz != nullptr) {
@@ -193,10 +225,13 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ dy_cls, int
           load8f(word + id * H + c, w); load8f(pos + pp * H + c, p8); load8f(type + tt * H + c, t8);
 #pragma unroll
           for (int j = 0; j < 8; ++j) x[j] = (w[j] + t8[j]) + p8[j];
+        } else if (dense_path) {
+          unpack8(cz[i], x);
         } else {
           load8(z + (long long)row * H + c, x);
         }
         if (sparse_dy) load8f(dy_cls + (long long)(row / cls_stride) * H + c, d[i]);
+        else if (dense_path) unpack8(cdy[i], d[i]);
         else load8(dy + (long long)row * H + c, d[i]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {

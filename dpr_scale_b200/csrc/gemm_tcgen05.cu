@@ -30,7 +30,9 @@ constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512 = all of TMEM
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;  // warps 0..3: TMA, MMA, TMEM alloc, spare
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int SLAB_BYTES = 32 * 128;  // 32 rows x 64 bf16, 128B-swizzled: one TMA-store box per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * SLAB_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
 
 struct GemmParams {
   int M, N, K;
@@ -49,13 +51,15 @@ struct GemmParams {
 template <int A_MN, int B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_d2,
                  const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B needs 1024-byte aligned tiles.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* smem_stage = smem + STAGES * STAGE_BYTES;  // [NUM_EPI_WARPS][SLAB_BYTES] epilogue staging slabs
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + NUM_EPI_WARPS * SLAB_BYTES);
   uint64_t* full_bar = bars;                       // [STAGES]
   uint64_t* empty_bar = bars + STAGES;             // [STAGES]
   uint64_t* tmem_full_bar = bars + 2 * STAGES;     // [ACC_STAGES]
@@ -68,6 +72,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_d);
+    tma_prefetch_desc(&tmap_d2);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -165,9 +171,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     __syncwarp();
   } else if (warp >= 4) {
     // ================================ epilogue warps ================================
+    // Warp (quarter, col_half) owns TMEM lanes [32*quarter, +32) x columns [128*col_half, +128) of the tile.
+    // bf16 outputs: registers -> 128B-swizzled smem slab (32 rows x 64 cols) -> TMA store (full-line writes;
+    // partial tiles are clipped by the tensor map).  aux (residual / pre-activation) is read with coalesced
+    // 16-byte loads through the same slab.  fp32 outputs (split-K wgrad) go out as RED/ST from registers.
     const int ew = warp - 4;
-    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
-    const int col_half = ew >> 2;          // which 128-column half of the 256-wide tile
+    const int quarter = warp & 3;
+    const int col_half = ew >> 2;
+    uint8_t* slab = smem_stage + ew * SLAB_BYTES;
+    const uint32_t slab_u32 = smem_u32(slab);
+    const bool f32_out = (p.epilogue == DPRB_EPI_F32_ATOMIC_ADD || p.epilogue == DPRB_EPI_F32_STORE);
+    const bool has_aux = (p.epilogue == DPRB_EPI_BIAS_RESIDUAL || p.epilogue == DPRB_EPI_DGELU);
+    const bool is_gelu = (p.epilogue == DPRB_EPI_BIAS_GELU);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -175,113 +190,128 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
-      const int row = m_blk * BLOCK_M + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int row0 = m_blk * BLOCK_M + quarter * 32;
+      const int row = row0 + lane;
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + col_half * 128);
+      if (f32_out) {
+        const bool row_ok = row < p.M;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int col0 = n_blk * BLOCK_N + col_half * 128 + c * 32;
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + col_half * 128 + c * 32);
-        tmem_ld_32x32(taddr, r);
-        tmem_ld_wait();
-        if (col0 < p.N) {  // warp-uniform
-        float v[32];
+        for (int c = 0; c < 4; ++c) {
+          const int col0 = n_blk * BLOCK_N + col_half * 128 + c * 32;
+          uint32_t r[32];
+          tmem_ld_32x32(tbase + c * 32, r);
+          tmem_ld_wait();
+          if (col0 < p.N && row_ok) {
+            float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-        const bool full = (col0 + 32 <= p.N);
-        if (p.bias != nullptr) {
-          if (full) {
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+            const bool full = (col0 + 32 <= p.N);
+            float* dst = reinterpret_cast<float*>(p.D) + (long long)row * p.ldd + col0;
+            if (p.epilogue == DPRB_EPI_F32_ATOMIC_ADD) {
+              if (full) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                for (int j = 0; j < 32; j += 4) red_add_v4_f32(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (col0 + j < p.N) atomicAdd(dst + j, v[j]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) dst[j] = v[j] + (p.bias != nullptr ? __ldg(p.bias + col0 + j) : 0.f);
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
           }
+          __syncwarp();  // reconverge before the next .sync.aligned tcgen05.ld
         }
-        if (row_ok) {
-        if (p.epilogue == DPRB_EPI_F32_ATOMIC_ADD) {
-          float* dst = reinterpret_cast<float*>(p.D) + (long long)row * p.ldd + col0;
-          if (full) {
+      } else {
+        const int n_pass = (is_gelu && p.out2 != nullptr) ? 2 : 1;  // GELU: pass 0 stores the pre-activation
+#pragma unroll 1
+        for (int sl = 0; sl < 2; ++sl) {          // two 64-column slabs per warp
+          const int colbase = n_blk * BLOCK_N + col_half * 128 + sl * 64;
+          if (colbase >= p.N) break;              // warp-uniform
+#pragma unroll 1
+          for (int pass = 0; pass < n_pass; ++pass) {
+            const bool store_pre = is_gelu && n_pass == 2 && pass == 0;
+            // the previous TMA store must have finished READING the slab before it is overwritten
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+            if (has_aux) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) red_add_v4_f32(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
+              for (int i = 0; i < 8; ++i) {
+                const int idx = lane + 32 * i, r = idx >> 3, ch = idx & 7;
+                uint4 q = make_uint4(0, 0, 0, 0);
+                if (row0 + r < p.M && colbase + ch * 8 < p.N)
+                  q = ldg_nc_v4(p.aux + (long long)(row0 + r) * p.ld_aux + colbase + ch * 8);
+                *reinterpret_cast<uint4*>(slab + r * 128 + ((ch ^ (r & 7)) << 4)) = q;
+              }
+              __syncwarp();
+            }
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {         // 32 accumulator columns at a time
+              const int col0 = colbase + h * 32;
+              uint32_t r[32];
+              tmem_ld_32x32(tbase + sl * 64 + h * 32, r);
+              tmem_ld_wait();
+              float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (col0 + j < p.N) atomicAdd(dst + j, v[j]);
-          }
-        } else if (p.epilogue == DPRB_EPI_F32_STORE) {
-          float* dst = reinterpret_cast<float*>(p.D) + (long long)row * p.ldd + col0;
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+              if (p.bias != nullptr) {
+                if (col0 + 32 <= p.N) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if (col0 + j < p.N) dst[j] = v[j];
-        } else {
-        bf16* dst = reinterpret_cast<bf16*>(p.D) + (long long)row * p.ldd + col0;
-        if (p.epilogue == DPRB_EPI_BIAS_RESIDUAL || p.epilogue == DPRB_EPI_DGELU) {
-          const bf16* ax = p.aux + (long long)row * p.ld_aux + col0;
-          if (full) {
+                  for (int j = 0; j < 32; j += 4) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                    v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                  }
+                } else {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 q = ldg_nc_v4(ax + j);
-              float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z), f3 = unpack_bf16x2(q.w);
-              float a[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+                  for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+                }
+              }
+              if (has_aux) {
 #pragma unroll
-              for (int t = 0; t < 8; ++t) {
-                if (p.epilogue == DPRB_EPI_BIAS_RESIDUAL) v[j + t] += a[t];
-                else v[j + t] *= gelu_erf_grad(a[t]);
+                for (int c4 = 0; c4 < 4; ++c4) {
+                  const int ch = h * 4 + c4;
+                  const uint4 q = *reinterpret_cast<const uint4*>(slab + lane * 128 + ((ch ^ (lane & 7)) << 4));
+                  const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z), f3 = unpack_bf16x2(q.w);
+                  const float a[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+#pragma unroll
+                  for (int t = 0; t < 8; ++t) {
+                    if (p.epilogue == DPRB_EPI_BIAS_RESIDUAL) v[c4 * 8 + t] += a[t];
+                    else v[c4 * 8 + t] *= gelu_erf_grad(a[t]);
+                  }
+                }
+              }
+              if (is_gelu && !store_pre) {
+                // GELU acts on the bf16-rounded pre-activation: backward re-reads exactly that value
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = gelu_erf(__bfloat162float(__float2bfloat16(v[j])));
+              }
+#pragma unroll
+              for (int c4 = 0; c4 < 4; ++c4) {
+                const int ch = h * 4 + c4;
+                uint4 q;
+                q.x = pack_bf16x2(v[c4 * 8 + 0], v[c4 * 8 + 1]); q.y = pack_bf16x2(v[c4 * 8 + 2], v[c4 * 8 + 3]);
+                q.z = pack_bf16x2(v[c4 * 8 + 4], v[c4 * 8 + 5]); q.w = pack_bf16x2(v[c4 * 8 + 6], v[c4 * 8 + 7]);
+                *reinterpret_cast<uint4*>(slab + lane * 128 + ((ch ^ (lane & 7)) << 4)) = q;
               }
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (col0 + j < p.N) {
-              float a = __bfloat162float(ax[j]);
-              if (p.epilogue == DPRB_EPI_BIAS_RESIDUAL) v[j] += a; else v[j] *= gelu_erf_grad(a);
+            fence_proxy_async_smem();   // make the generic-proxy smem writes visible to the TMA engine
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(store_pre ? &tmap_d2 : &tmap_d, slab_u32, colbase, row0);
+              tma_store_commit();
             }
           }
         }
-        if (p.epilogue == DPRB_EPI_BIAS_GELU) {
-          bf16* pre = p.out2 + (long long)row * p.ldd + col0;
-          if (p.out2 == nullptr) {
-            // forward-only (generate_embeddings) path: the pre-activation is not kept
-          } else if (full) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 q;
-              q.x = pack_bf16x2(v[j], v[j + 1]); q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-              q.z = pack_bf16x2(v[j + 4], v[j + 5]); q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-              *reinterpret_cast<uint4*>(pre + j) = q;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (col0 + j < p.N) pre[j] = __float2bfloat16(v[j]);
-          }
-          // GELU is applied to the bf16-rounded pre-activation so that backward (which re-reads the
-          // stored bf16 value) differentiates exactly the function forward evaluated.
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(__bfloat162float(__float2bfloat16(v[j])));
-        }
-        if (full) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 q;
-            q.x = pack_bf16x2(v[j], v[j + 1]); q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-            q.z = pack_bf16x2(v[j + 4], v[j + 5]); q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-            *reinterpret_cast<uint4*>(dst + j) = q;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (col0 + j < p.N) dst[j] = __float2bfloat16(v[j]);
-        }
-        }  // bf16 epilogues
-        }  // row_ok
-        }  // col0 < N
-        __syncwarp();  // reconverge before the next .sync.aligned tcgen05.ld
+        __syncwarp();
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) tma_store_wait_all();  // smem must stay valid until the last bulk store has drained
+    __syncwarp();
   }
 
   tcgen05_fence_before();
@@ -311,7 +341,8 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // Row-major bf16 matrix [rows, cols] with leading dimension ld (elements); box = [box_rows, 64 cols], 128B swizzle.
-int make_tmap(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+int make_tmap(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld, int box_rows,
+              bool is_output = false) {
   EncodeTiledFn fn = get_encode_fn();
   DPRB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   DPRB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "gemm operand base %p not 16-byte aligned", base);
@@ -321,7 +352,8 @@ int make_tmap(CUtensorMap* out, const void* base, long long rows, long long cols
   cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  is_output ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DPRB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)",
                (int)r, rows, cols, ld);
@@ -372,6 +404,19 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long l
   if (rc) return rc;
   if (!b_mn_major) rc = make_tmap(&tb, B, N, K, ldb, BLOCK_N); else rc = make_tmap(&tb, B, K, N, ldb, BLOCK_K);
   if (rc) return rc;
+  CUtensorMap td, td2;
+  if (!f32_out) {
+    if ((rc = make_tmap(&td, D, M, N, ldd, 32, true))) return rc;
+    if (epilogue == DPRB_EPI_BIAS_GELU && out2 != nullptr) {
+      DPRB_REQUIRE((reinterpret_cast<uintptr_t>(out2) & 15) == 0, "gemm: out2 not 16-byte aligned");
+      if ((rc = make_tmap(&td2, out2, M, N, ldd, 32, true))) return rc;
+    } else {
+      td2 = td;
+    }
+  } else {
+    td = ta;  // unused by the fp32 epilogues; any valid descriptor
+    td2 = ta;
+  }
 
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
@@ -392,15 +437,18 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long l
   const int units = tiles * p.splits;
   const int grid = units < sms ? units : sms;
 
+  static bool attr_set = false;
+  if (!attr_set) {
+    DPRB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DPRB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DPRB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DPRB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
   auto launch = [&](auto kern) -> int {
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
-      DPRB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      attr_set = true;
-    }
     const bool prof = g_prof.enabled && g_prof.used + 2 <= g_prof.ev.size();
     if (prof) DPRB_CHECK_CUDA(cudaEventRecord(g_prof.ev[g_prof.used], stream));
-    kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+    kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, td, td2, p);
     DPRB_CHECK_CUDA(cudaGetLastError());
     if (prof) {
       DPRB_CHECK_CUDA(cudaEventRecord(g_prof.ev[g_prof.used + 1], stream));

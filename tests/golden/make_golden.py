@@ -11,7 +11,8 @@ The reference cannot travel to the GPU box, so the vectors are committed.  What 
     torch.stack(dim=0) under no_grad; identity when not distributed.
 Cases:
   golden_1rank.npz  BERT (vocab 64, H128, L2, A2, I256), 4 queries, 1 pos + 1 neg, padded sequences,
-                    one dummy (masked) negative, temperature 0.5 — embeddings, logits, loss, all grads.
+                    one dummy (masked) negative, temperature 8 (keeps the tiny random model's logits O(10),
+                    away from the saturated-softmax regime where a 0.3 % bf16 logit error swings probabilities by e^1) — embeddings, logits, loss, all grads.
   golden_2rank.npz  same model, world_size 2 (gloo): per-rank loss and per-rank grads (global in-batch negatives).
   golden_roberta.npz RoBERTa-style (pad_id 1, position ids from cumsum) encoder forward only.
 """
@@ -174,7 +175,7 @@ def run_rank(rank, world, qdir, cdir, port, ret):
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
         dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.manual_seed(0)
-    T = 0.5
+    T = 8.0
     task = build_task(qdir, cdir, DDPStrategy, world > 1, T)
     batch = make_batch(rank)
     loss = task.training_step(batch, 0)
@@ -196,6 +197,27 @@ def run_rank(rank, world, qdir, cdir, port, ret):
             for k, v in enc.state_dict().items():
                 out[f"sd_{name}/{k}"] = v.numpy()
         out["temperature"] = np.float32(T)
+        # The reference's OWN mixed-precision deviation on this batch (Lightning `precision: 16` analogue; bf16
+        # autocast because fp16 matmul is not available on CPU): same weights, same batch, gradients compared
+        # with the fp32 run above.  Stored so the CUDA-path tolerances can be stated relative to it.
+        fp32_grads = {f"{n}/{k}": p.grad.clone() for n, e in (("q", task.query_encoder), ("c", task.context_encoder))
+                      for k, p in e.named_parameters() if p.grad is not None}
+        task.zero_grad()
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            amp_loss = task.training_step(batch, 0)
+        amp_loss.backward()
+        out["amp_loss"] = amp_loss.detach().float().numpy()
+        num = den = 0.0
+        for n, e in (("q", task.query_encoder), ("c", task.context_encoder)):
+            for k, p in e.named_parameters():
+                if p.grad is None:
+                    continue
+                a, b = p.grad.double().flatten(), fp32_grads[f"{n}/{k}"].double().flatten()
+                out[f"amp_cos_{n}/{k}"] = np.float64((a @ b) / (a.norm() * b.norm() + 1e-30))
+                out[f"amp_rel_{n}/{k}"] = np.float64((a - b).norm() / (b.norm() + 1e-30))
+                num += float(((a - b) ** 2).sum())
+                den += float((b ** 2).sum())
+        out["amp_global_rel"] = np.float64((num / den) ** 0.5)
     ret[rank] = out
     if world > 1:
         dist.barrier()

@@ -47,7 +47,7 @@ def test_gather_semantics_match_reference_2rank():
             labs.append(b["pos_ctx_indices"])
             masks.append(b["ctx_mask"])
         q, c, lab, m = otask.gather_for_rank(rank, qs, cs, labs, masks)
-        loss, _ = otask.in_batch_loss(q, c, m, lab, 0.5)
+        loss, _ = otask.in_batch_loss(q, c, m, lab, float(g1["temperature"]))
         assert abs(float(loss) - float(g[f"rank{rank}/loss"])) < 1e-5
         loss.backward()
         for name, sd in (("q", sd_q), ("c", sd_c)):

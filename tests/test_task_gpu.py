@@ -3,8 +3,14 @@ against golden vectors produced by the unmodified reference (tests/golden/make_g
 
 Tolerances (vs the fp32 reference; SURVEY.md §8c — the reference's own bf16 autocast deviates by emb rel-L2
 5.5e-3, logits 3.5e-3 relative, loss 0.018):
-  embeddings rel-L2 <= 1e-2 ; logits max-abs <= 1e-2 * max|logit| ; loss abs <= 5e-2 ;
-  per-parameter gradient cosine >= 0.99 (>= 0.999 for the large matrices), gradient rel-L2 <= 5e-2.
+  embeddings rel-L2 <= 1e-2 ; logits max-abs <= 1e-2 * max|logit| ; loss abs <= 5e-2.
+Gradients are checked twice:
+  * well-conditioned (linear probe on the embeddings): per-parameter cosine >= 0.9995, rel-L2 <= 2e-2;
+  * full contrastive step: at random init the CLS embeddings of different inputs are almost collinear and
+    sum_j dL/dc_j = 0, so parameter gradients are small residuals of large cancelling terms and ANY 16-bit
+    activation path sees its ~0.5 % error amplified ~40x.  The golden file records what the reference's own
+    bf16 autocast does on this batch (per-tensor rel-L2 0.02..0.63, global 0.18); the CUDA path must stay
+    within 2x of that per tensor and within 1.5x globally — i.e. no looser than the reference's own AMP.
 """
 import pytest
 import torch
@@ -17,7 +23,8 @@ CFG = dict(vocab_size=64, hidden_size=128, num_hidden_layers=2, num_attention_he
            max_position_embeddings=40)
 
 
-def _task(g, temperature=0.5):
+def _task(g, temperature=None):
+    temperature = float(g["temperature"]) if temperature is None else temperature
     from dpr_scale_b200.models.hf_model import HFEncoder
     from dpr_scale_b200.task.dpr_task import DenseRetrieverTask
     task = DenseRetrieverTask(transform={}, model={"_target_": "dpr_scale_b200.models.hf_model.HFEncoder.from_config",
@@ -42,41 +49,84 @@ def test_state_dict_keys_match_reference():
     assert set(task.query_encoder.state_dict()) == set(sub(g, "sd_q/"))
 
 
+def _grad_report(task_grads, ref_grads):
+    """per-parameter (name, cosine, rel-L2, numel, ref norm) of CUDA-path grads vs reference grads"""
+    rows = []
+    top = max(float(r.norm()) for r in ref_grads.values())
+    for k, r in ref_grads.items():
+        got = task_grads[k]
+        assert got is not None, k
+        got = got.detach().float().cpu()
+        if float(r.norm()) < 1e-5 * top:
+            # analytically-zero gradients (e.g. key.bias: softmax is shift invariant) — only bound the noise
+            assert float(got.norm()) < 1e-2 * top, (k, float(got.norm()), top)
+            continue
+        rows.append((k, cosine(got, r), rel_l2(got, r), r.numel(), float(r.norm())))
+    return rows
+
+
+def test_encoder_forward_backward_match_oracle_linear_probe():
+    """Encoder fwd+bwd alone: L = sum(rep * P) with a fixed probe P is linear in the embeddings, so parameter
+    gradients are compared without the cancellation of the contrastive loss amplifying bf16 noise."""
+    from oracle import encoder as oenc
+    from tests.util import BERT_TINY_CFG
+    g = load_golden("golden_1rank.npz")
+    task = _task(g)
+    enc = task.context_encoder
+    tokens = _batch(g)["contexts_ids"]
+    probe = torch.randn(8, 128, generator=torch.Generator().manual_seed(3))
+    sd = {k: v.clone().requires_grad_(True) for k, v in sub(g, "sd_c/").items()}
+    ref_rep = oenc.encode(sd, BERT_TINY_CFG, tokens)
+    (ref_rep * probe).sum().backward()
+    enc.zero_grad()
+    rep = enc(tokens)
+    assert rel_l2(rep.detach().cpu(), ref_rep.detach()) <= 1e-2
+    (rep * probe.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    rows = _grad_report({k: p.grad for k, p in enc.named_parameters()},
+                        {k: v.grad for k, v in sd.items() if v.grad is not None and "pooler" not in k})
+    assert len(rows) >= 34
+    print("encoder probe: worst cosine", min(rows, key=lambda r: r[1]))
+    for k, cs, rl, n, _ in rows:
+        assert cs >= 0.9995, (k, cs, rl)
+        assert rl <= 2e-2, (k, cs, rl)
+
+
 def test_training_step_matches_reference_golden():
     g = load_golden("golden_1rank.npz")
+    T = float(g["temperature"])
     task = _task(g)
     batch = _batch(g)
     with torch.no_grad():
         q, c = task(batch["query_ids"], batch["contexts_ids"])
     assert rel_l2(q.cpu(), g["q_emb"]) <= 1e-2, rel_l2(q.cpu(), g["q_emb"])
     assert rel_l2(c.cpu(), g["c_emb"]) <= 1e-2
+    for e in (task.query_encoder, task.context_encoder):
+        e.zero_grad()
     loss = task.training_step(batch, 0)
     assert abs(float(loss) - float(g["loss"])) <= 5e-2, (float(loss), float(g["loss"]))
+    assert abs(float(loss) - float(g["loss"])) <= 2 * abs(float(g["amp_loss"]) - float(g["loss"])) + 1e-3
     loss.backward()
     torch.cuda.synchronize()
     m = batch["ctx_mask"].repeat(q.shape[0], 1)
-    logits = task.sim_score(q, c, m.cuda()).cpu() / 0.5
+    logits = task.sim_score(q, c, m.cuda()).cpu() / T
     fin = torch.isfinite(g["logits"])
     assert torch.equal(torch.isfinite(logits), fin)
     assert float((logits[fin] - g["logits"][fin]).abs().max()) <= 1e-2 * float(g["logits"][fin].abs().max())
-    worst = 1.0
+    num = den = 0.0
     for name, enc in (("q", task.query_encoder), ("c", task.context_encoder)):
-        ref = sub(g, f"grad_{name}/")
         params = dict(enc.named_parameters())
-        for k, r in ref.items():
-            got = params[k].grad
-            assert got is not None, k
-            got = got.detach().cpu()
-            if float(r.norm()) < 1e-7:
-                assert float(got.norm()) < 1e-5, k
-                continue
-            cs = cosine(got, r)
-            worst = min(worst, cs)
-            assert cs >= (0.999 if r.numel() >= 128 * 128 else 0.99), (name, k, cs)
-            assert rel_l2(got, r) <= 5e-2, (name, k, rel_l2(got, r))
-        # pooler receives no gradient in the reference either
-        assert params["transformer.pooler.dense.weight"].grad is None
-    print("worst gradient cosine", worst)
+        ref = sub(g, f"grad_{name}/")
+        rows = _grad_report({k: p.grad for k, p in params.items()}, ref)
+        assert params["transformer.pooler.dense.weight"].grad is None  # no grad in the reference either
+        for k, cs, rl, n, rn in rows:
+            amp_rel = float(g[f"amp_rel_{name}/{k}"])
+            assert rl <= max(5e-2, 2.0 * amp_rel), (name, k, "rel", rl, "reference AMP rel", amp_rel, "cos", cs)
+            num += (rl * rn) ** 2
+            den += rn ** 2
+    global_rel = (num / den) ** 0.5
+    print("full step: global gradient rel-L2", global_rel, "reference bf16-autocast:", float(g["amp_global_rel"]))
+    assert global_rel <= 1.5 * float(g["amp_global_rel"])
 
 
 def test_non_in_batch_branch_matches_oracle():

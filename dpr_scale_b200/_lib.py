@@ -48,7 +48,7 @@ SIGNATURES = {
     "dprb_last_error": (c_char_p, []),
     "dprb_num_sms": (c_int, []),
     "dprb_gemm_bf16": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_int, c_int,
-                               _P, _P, c_int64, _P, c_float, c_int, _P]),
+                               _P, _P, c_int64, _P, c_float, c_int, _P, _P]),
     "dprb_gemm_profile_enable": (c_int, [c_int, c_int]),
     "dprb_gemm_profile_read": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int64)]),
     "dprb_embed_ln_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,

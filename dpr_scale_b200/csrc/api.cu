@@ -40,9 +40,9 @@ int dprb_num_sms(void) { return num_sms(); }
 
 int dprb_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int64_t lda, int64_t ldb,
                    int64_t ldd, int a_mn_major, int b_mn_major, int epilogue, const float* bias, const void* aux,
-                   int64_t ld_aux, void* out2, float alpha, int splits, dprb_stream_t stream) {
+                   int64_t ld_aux, void* out2, float alpha, int splits, float* colsum, dprb_stream_t stream) {
   return gemm_bf16(A, B, D, M, N, K, lda, ldb, ldd, a_mn_major, b_mn_major, epilogue, bias, aux, ld_aux, out2,
-                   alpha, splits, S(stream));
+                   alpha, splits, colsum, S(stream));
 }
 
 int dprb_gemm_profile_enable(int enable, int max_launches) { return gemm_profile_enable(enable, max_launches); }

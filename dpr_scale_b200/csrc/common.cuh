@@ -76,14 +76,37 @@ __device__ __forceinline__ float erf_as(float x) {
   float r = fmaf(-p, e, 1.0f);
   return copysignf(r, x);
 }
-__device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f));
+// Gaussian CDF Phi(x) as a logistic of an odd degree-5 polynomial (least-squares fit on [-6,6], argument clamped
+// to [-8,8]): max |Phi err| 5.8e-5, max |x*Phi - gelu_erf(x)| 3.0e-5 over all x — two orders of magnitude below the
+// bf16 rounding of the stored activation.  11 instructions / 2 MUFU per element instead of ~24 / 2 for erf_as():
+// at K = 768 the FFN GEMM epilogue has only ~24 issue slots per output element before it, not the tensor pipe,
+// bounds the kernel.  The same Phi is used by forward and backward, so backward differentiates what forward computed
+// (up to the 3e-5 fit error of x*Phi vs its exact derivative Phi + x*phi).
+// single-MUFU approximations (ex2.approx / rcp.approx: ~2 ulp), no denormal / range fix-up code
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gauss_cdf(float x) {
+  const float xc = fminf(fmaxf(x, -8.f), 8.f);
+  const float x2 = xc * xc;
+  // -log2(e) * (1.59492135 + 0.0740977934 x^2 - 0.000717098742 x^4)
+  float pz = fmaf(x2, 1.03455483e-3f, -1.06900513e-1f);
+  pz = fmaf(pz, x2, -2.30098511f);
+  const float e = ex2_approx(pz * xc);      // exp(-z); |z| <= 47 after the clamp: no overflow
+  return rcp_approx(1.f + e);
+}
+__device__ __forceinline__ float gelu_erf(float x) { return x * gauss_cdf(x); }
 // d/dx gelu(x) = Phi(x) + x * phi(x)
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  float cdf = 0.5f * (1.0f + erf_as(x * 0.70710678118654752f));
-  float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
-  return fmaf(x, pdf, cdf);
+  const float pdf = 0.39894228040143268f * ex2_approx(-0.72134752044448170f * x * x);
+  return fmaf(x, pdf, gauss_cdf(x));
 }
 
 // Counter-based dropout RNG: one 32-bit hash per element index.  keep iff u >= p.

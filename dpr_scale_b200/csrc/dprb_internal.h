@@ -7,7 +7,7 @@ namespace dprb {
 
 int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long long lda, long long ldb,
               long long ldd, int a_mn_major, int b_mn_major, int epilogue, const float* bias, const void* aux,
-              long long ld_aux, void* out2, float alpha, int splits, cudaStream_t stream);
+              long long ld_aux, void* out2, float alpha, int splits, float* colsum, cudaStream_t stream);
 
 int gemm_profile_enable(int enable, int max_launches);
 int gemm_profile_read(double* total_ms, double* total_flops, long long* launches);

@@ -121,12 +121,12 @@ int encoder_fwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b, floa
   for (int l = 0; l < L; ++l) {
     const LayerW lw = layer_w(w, l);
     LayerActs& a = ws.slot[b->save_for_backward ? l : (l & 1)];
-    TRY(gemm_bf16(x, lw.wqkv, a.qkv, T, 3 * H, H, H, H, 3 * H, 0, 0, DPRB_EPI_BIAS, lw.bqkv, nullptr, 0, nullptr, 1.f, 1, stream));
+    TRY(gemm_bf16(x, lw.wqkv, a.qkv, T, 3 * H, H, H, H, 3 * H, 0, 0, DPRB_EPI_BIAS, lw.bqkv, nullptr, 0, nullptr, 1.f, 1, nullptr, stream));
     TRY(attn_fwd_lse(a.qkv, b->attn_mask, a.ctx, a.lse, b->nseq, b->S, w->heads, stream));
-    TRY(gemm_bf16(a.ctx, lw.wo, a.z1, T, H, H, H, H, H, 0, 0, DPRB_EPI_BIAS_RESIDUAL, lw.bo, x, H, nullptr, 1.f, 1, stream));
+    TRY(gemm_bf16(a.ctx, lw.wo, a.z1, T, H, H, H, H, H, 0, 0, DPRB_EPI_BIAS_RESIDUAL, lw.bo, x, H, nullptr, 1.f, 1, nullptr, stream));
     TRY(ln_fwd(a.z1, lw.ln1g, lw.ln1b, a.x1, a.stats1, nullptr, 1, T, H, w->ln_eps, stream));
-    TRY(gemm_bf16(a.x1, lw.w1, a.hact, T, I, H, H, H, I, 0, 0, DPRB_EPI_BIAS_GELU, lw.b1, nullptr, 0, a.hpre, 1.f, 1, stream));
-    TRY(gemm_bf16(a.hact, lw.w2, a.z2, T, H, I, I, I, H, 0, 0, DPRB_EPI_BIAS_RESIDUAL, lw.b2, a.x1, H, nullptr, 1.f, 1, stream));
+    TRY(gemm_bf16(a.x1, lw.w1, a.hact, T, I, H, H, H, I, 0, 0, DPRB_EPI_BIAS_GELU, lw.b1, nullptr, 0, a.hpre, 1.f, 1, nullptr, stream));
+    TRY(gemm_bf16(a.hact, lw.w2, a.z2, T, H, I, I, I, H, 0, 0, DPRB_EPI_BIAS_RESIDUAL, lw.b2, a.x1, H, nullptr, 1.f, 1, nullptr, stream));
     const bool last = (l == L - 1);
     TRY(ln_fwd(a.z2, lw.ln2g, lw.ln2b, a.out, a.stats2, last ? pooled : nullptr, b->S, T, H, w->ln_eps, stream));
     x = a.out;
@@ -153,26 +153,28 @@ int encoder_bwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b, cons
     TRY(ln_bwd(last ? nullptr : ws.gA, last ? dpooled : nullptr, b->S, a.z2, a.stats2, lw.ln2g, ws.gB, lw.g_ln2g,
                lw.g_ln2b, lw.g_b2, T, H, stream));
     // dW2 += dz2^T hact
-    TRY(gemm_bf16(ws.gB, a.hact, lw.g_w2, H, I, T, H, I, I, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, stream));
+    TRY(gemm_bf16(ws.gB, a.hact, lw.g_w2, H, I, T, H, I, I, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, stream));
     // dhpre = (dz2 W2) * gelu'(hpre)
-    TRY(gemm_bf16(ws.gB, lw.w2, ws.gH, T, I, H, H, I, I, 0, 1, DPRB_EPI_DGELU, nullptr, a.hpre, I, nullptr, 1.f, 1, stream));
+    TRY(gemm_bf16(ws.gB, lw.w2, ws.gH, T, I, H, H, I, I, 0, 1, DPRB_EPI_DGELU, nullptr, a.hpre, I, nullptr, 1.f, 1, nullptr, stream));
+    // db1: a separate streaming pass (127 us) is cheaper than the fused epilogue column sums (+143 us) here,
+    // because this GEMM's epilogue (dGELU, 3 MUFU/element) is already its critical path.
     TRY(colsum_bf16(ws.gH, I, lw.g_b1, T, I, stream));
     // dW1 += dhpre^T x1
-    TRY(gemm_bf16(ws.gH, a.x1, lw.g_w1, I, H, T, I, H, H, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, stream));
+    TRY(gemm_bf16(ws.gH, a.x1, lw.g_w1, I, H, T, I, H, H, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, stream));
     // dx1 = dhpre W1 + dz2
-    TRY(gemm_bf16(ws.gH, lw.w1, ws.gA, T, H, I, I, H, H, 0, 1, DPRB_EPI_BIAS_RESIDUAL, nullptr, ws.gB, H, nullptr, 1.f, 1, stream));
+    TRY(gemm_bf16(ws.gH, lw.w1, ws.gA, T, H, I, I, H, H, 0, 1, DPRB_EPI_BIAS_RESIDUAL, nullptr, ws.gB, H, nullptr, 1.f, 1, nullptr, stream));
     // LN1 backward (+ dbo)
     TRY(ln_bwd(ws.gA, nullptr, 1, a.z1, a.stats1, lw.ln1g, ws.gB, lw.g_ln1g, lw.g_ln1b, lw.g_bo, T, H, stream));
     // dWo += dz1^T ctx
-    TRY(gemm_bf16(ws.gB, a.ctx, lw.g_wo, H, H, T, H, H, H, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, stream));
+    TRY(gemm_bf16(ws.gB, a.ctx, lw.g_wo, H, H, T, H, H, H, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, stream));
     // dctx = dz1 Wo
-    TRY(gemm_bf16(ws.gB, lw.wo, ws.gA, T, H, H, H, H, H, 0, 1, DPRB_EPI_BIAS, nullptr, nullptr, 0, nullptr, 1.f, 1, stream));
+    TRY(gemm_bf16(ws.gB, lw.wo, ws.gA, T, H, H, H, H, H, 0, 1, DPRB_EPI_BIAS, nullptr, nullptr, 0, nullptr, 1.f, 1, nullptr, stream));
     TRY(attn_bwd_lse(a.qkv, b->attn_mask, a.ctx, a.lse, ws.gA, ws.gQKV, b->nseq, b->S, w->heads, stream));
     TRY(colsum_bf16(ws.gQKV, 3 * H, lw.g_bqkv, T, 3 * H, stream));
     // dWqkv += dqkv^T x
-    TRY(gemm_bf16(ws.gQKV, x, lw.g_wqkv, 3 * H, H, T, 3 * H, H, H, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, stream));
+    TRY(gemm_bf16(ws.gQKV, x, lw.g_wqkv, 3 * H, H, T, 3 * H, H, H, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, stream));
     // dx = dqkv Wqkv + dz1
-    TRY(gemm_bf16(ws.gQKV, lw.wqkv, ws.gA, T, H, 3 * H, 3 * H, H, H, 0, 1, DPRB_EPI_BIAS_RESIDUAL, nullptr, ws.gB, H, nullptr, 1.f, 1, stream));
+    TRY(gemm_bf16(ws.gQKV, lw.wqkv, ws.gA, T, H, 3 * H, 3 * H, H, H, 0, 1, DPRB_EPI_BIAS_RESIDUAL, nullptr, ws.gB, H, nullptr, 1.f, 1, nullptr, stream));
   }
   if (layer_lo == 0) {
     const float* ms = w->master;

@@ -46,6 +46,7 @@ struct GemmParams {
   long long ld_aux;
   bf16* out2;          // EPI_BIAS_GELU: pre-activation store, ld = ldd
   float alpha;         // scale applied to the accumulator before the epilogue
+  float* colsum;       // optional: colsum[n] += sum_m D(m, n) of the bf16-rounded output (bias gradients)
 };
 
 template <int A_MN, int B_MN>
@@ -223,15 +224,67 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           __syncwarp();  // reconverge before the next .sync.aligned tcgen05.ld
         }
+      } else if (is_gelu) {
+        // single pass, two 32x32 slabs (64B swizzle): pre-activation -> out2 (optional), GELU -> D
+        uint8_t* slab_pre = slab;
+        uint8_t* slab_act = slab + SLAB_BYTES / 2;
+#pragma unroll 1
+        for (int h = 0; h < 4; ++h) {
+          const int col0 = n_blk * BLOCK_N + col_half * 128 + h * 32;
+          if (col0 >= p.N) break;  // warp-uniform
+          uint32_t r[32];
+          tmem_ld_32x32(tbase + h * 32, r);
+          tmem_ld_wait();
+          float v[32];
+          if (p.bias != nullptr && col0 + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+              v[j] = fmaf(__uint_as_float(r[j]), p.alpha, b.x); v[j + 1] = fmaf(__uint_as_float(r[j + 1]), p.alpha, b.y);
+              v[j + 2] = fmaf(__uint_as_float(r[j + 2]), p.alpha, b.z); v[j + 3] = fmaf(__uint_as_float(r[j + 3]), p.alpha, b.w);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] = fmaf(__uint_as_float(r[j]), p.alpha, (p.bias != nullptr && col0 + j < p.N) ? __ldg(p.bias + col0 + j) : 0.f);
+          }
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            uint4 qp, qa;
+            uint32_t* pp = &qp.x;
+            uint32_t* pa = &qa.x;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const uint32_t pre2 = pack_bf16x2(v[c4 * 8 + 2 * t], v[c4 * 8 + 2 * t + 1]);
+              // GELU acts on the bf16-rounded pre-activation: backward re-reads exactly that value
+              const float2 f = unpack_bf16x2(pre2);
+              pp[t] = pre2;
+              pa[t] = pack_bf16x2(gelu_erf(f.x), gelu_erf(f.y));
+            }
+            const uint32_t off = lane * 64 + ((c4 ^ ((lane >> 1) & 3)) << 4);
+            if (p.out2 != nullptr) *reinterpret_cast<uint4*>(slab_pre + off) = qp;
+            *reinterpret_cast<uint4*>(slab_act + off) = qa;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.out2 != nullptr) tma_store_2d(&tmap_d2, slab_u32, col0, row0);
+            tma_store_2d(&tmap_d, slab_u32 + SLAB_BYTES / 2, col0, row0);
+            tma_store_commit();
+          }
+        }
+        __syncwarp();
       } else {
-        const int n_pass = (is_gelu && p.out2 != nullptr) ? 2 : 1;  // GELU: pass 0 stores the pre-activation
+        const int n_pass = 1;
 #pragma unroll 1
         for (int sl = 0; sl < 2; ++sl) {          // two 64-column slabs per warp
           const int colbase = n_blk * BLOCK_N + col_half * 128 + sl * 64;
           if (colbase >= p.N) break;              // warp-uniform
 #pragma unroll 1
           for (int pass = 0; pass < n_pass; ++pass) {
-            const bool store_pre = is_gelu && n_pass == 2 && pass == 0;
+            const bool store_pre = false;
             // the previous TMA store must have finished READING the slab before it is overwritten
             if (lane == 0) tma_store_wait_read();
             __syncwarp();
@@ -281,11 +334,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                   }
                 }
               }
-              if (is_gelu && !store_pre) {
-                // GELU acts on the bf16-rounded pre-activation: backward re-reads exactly that value
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = gelu_erf(__bfloat162float(__float2bfloat16(v[j])));
-              }
 #pragma unroll
               for (int c4 = 0; c4 < 4; ++c4) {
                 const int ch = h * 4 + c4;
@@ -294,6 +342,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 q.z = pack_bf16x2(v[c4 * 8 + 4], v[c4 * 8 + 5]); q.w = pack_bf16x2(v[c4 * 8 + 6], v[c4 * 8 + 7]);
                 *reinterpret_cast<uint4*>(slab + lane * 128 + ((ch ^ (lane & 7)) << 4)) = q;
               }
+            }
+            if (p.colsum != nullptr) {
+              // column sums of the staged (bf16-rounded) slab: lane l owns columns 2l, 2l+1; conflict-free reads
+              __syncwarp();
+              const int nrows = min(32, p.M - row0);
+              float s0 = 0.f, s1 = 0.f;
+              for (int r = 0; r < nrows; ++r) {
+                const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(
+                    slab + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4));
+                s0 += f.x; s1 += f.y;
+              }
+              const int col = colbase + lane * 2;
+              if (col < p.N) atomicAdd(p.colsum + col, s0);
+              if (col + 1 < p.N) atomicAdd(p.colsum + col + 1, s1);
             }
             fence_proxy_async_smem();   // make the generic-proxy smem writes visible to the TMA engine
             __syncwarp();
@@ -342,17 +404,17 @@ EncodeTiledFn get_encode_fn() {
 
 // Row-major bf16 matrix [rows, cols] with leading dimension ld (elements); box = [box_rows, 64 cols], 128B swizzle.
 int make_tmap(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld, int box_rows,
-              bool is_output = false) {
+              bool is_output = false, int box_cols = 64) {
   EncodeTiledFn fn = get_encode_fn();
   DPRB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   DPRB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "gemm operand base %p not 16-byte aligned", base);
   DPRB_REQUIRE((ld * 2) % 16 == 0, "gemm operand leading dimension %lld not a multiple of 8 elements", ld);
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                   is_output ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DPRB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)",
@@ -386,7 +448,7 @@ int choose_splits(int tiles, int k_blocks, int sms) {
 
 int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long long lda, long long ldb,
               long long ldd, int a_mn_major, int b_mn_major, int epilogue, const float* bias, const void* aux,
-              long long ld_aux, void* out2, float alpha, int splits, cudaStream_t stream) {
+              long long ld_aux, void* out2, float alpha, int splits, float* colsum, cudaStream_t stream) {
   DPRB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   DPRB_REQUIRE(epilogue >= 0 && epilogue < DPRB_EPI_COUNT, "gemm: bad epilogue %d", epilogue);
   const bool f32_out = (epilogue == DPRB_EPI_F32_ATOMIC_ADD || epilogue == DPRB_EPI_F32_STORE);
@@ -406,10 +468,11 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long l
   if (rc) return rc;
   CUtensorMap td, td2;
   if (!f32_out) {
-    if ((rc = make_tmap(&td, D, M, N, ldd, 32, true))) return rc;
+    const int bc = (epilogue == DPRB_EPI_BIAS_GELU) ? 32 : 64;  // GELU epilogue stages two 32x32 slabs
+    if ((rc = make_tmap(&td, D, M, N, ldd, 32, true, bc))) return rc;
     if (epilogue == DPRB_EPI_BIAS_GELU && out2 != nullptr) {
       DPRB_REQUIRE((reinterpret_cast<uintptr_t>(out2) & 15) == 0, "gemm: out2 not 16-byte aligned");
-      if ((rc = make_tmap(&td2, out2, M, N, ldd, 32, true))) return rc;
+      if ((rc = make_tmap(&td2, out2, M, N, ldd, 32, true, bc))) return rc;
     } else {
       td2 = td;
     }
@@ -433,6 +496,9 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long l
   p.epilogue = epilogue;
   p.D = D; p.ldd = ldd; p.bias = bias; p.aux = reinterpret_cast<const bf16*>(aux); p.ld_aux = ld_aux;
   p.out2 = reinterpret_cast<bf16*>(out2); p.alpha = alpha;
+  p.colsum = colsum;
+  DPRB_REQUIRE(colsum == nullptr || (!f32_out && epilogue != DPRB_EPI_BIAS_GELU),
+               "gemm: colsum is supported for the BIAS / BIAS_RESIDUAL / DGELU epilogues only");
 
   const int units = tiles * p.splits;
   const int grid = units < sms ? units : sms;

@@ -30,10 +30,11 @@ def _stream():
 
 
 def gemm(a, b, out, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, epilogue=EPI_BIAS, bias=None, aux=None,
-         ld_aux=0, out2=None, alpha=1.0, splits=1):
+         ld_aux=0, out2=None, alpha=1.0, splits=1, colsum=None):
     lib = _lib.load()
     check(lib.dprb_gemm_bf16(_ptr(a), _ptr(b), _ptr(out), M, N, K, lda, ldb, ldd, int(a_mn), int(b_mn), epilogue,
-                             _ptr(bias), _ptr(aux), ld_aux, _ptr(out2), float(alpha), splits, _stream()),
+                             _ptr(bias), _ptr(aux), ld_aux, _ptr(out2), float(alpha), splits, _ptr(colsum),
+                             _stream()),
           "dprb_gemm_bf16")
     _count()
     return out

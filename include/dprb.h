@@ -37,6 +37,8 @@ int dprb_num_sms(void);
  * Replaces torch.nn.Linear forward/backward inside HF BertLayer:
  *   site-packages/transformers/models/bert/modeling_bert.py:179-181 (Q,K,V — fused here into one
  *   [3H,H] weight), :295 (attention output dense), :340 (intermediate dense), :353 (output dense).
+ * colsum (optional, bf16 epilogues except BIAS_GELU): colsum[n] += sum_m D(m,n) — the bias gradient of the
+ * Linear whose output gradient this GEMM produces, fused into the epilogue instead of a separate pass.
  * a_mn_major/b_mn_major = 0: operand stored [MN, K] (K contiguous, leading dim ld);
  *                       = 1: operand stored [K, MN] (MN contiguous, leading dim ld).
  * ------------------------------------------------------------------------------------------- */
@@ -51,7 +53,8 @@ enum {
 };
 int dprb_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int64_t lda, int64_t ldb,
                    int64_t ldd, int a_mn_major, int b_mn_major, int epilogue, const float* bias,
-                   const void* aux, int64_t ld_aux, void* out2, float alpha, int splits, dprb_stream_t stream);
+                   const void* aux, int64_t ld_aux, void* out2, float alpha, int splits, float* colsum,
+                   dprb_stream_t stream);
 
 /* Measurement aid (bench.py roofline leg): when enabled, every GEMM launch is bracketed by CUDA events on
  * its launch stream; dprb_gemm_profile_read sums the per-launch durations and algorithmic FLOPs (2*M*N*K). */

@@ -63,8 +63,9 @@ def check_gemm(M, N, K, a_mn=False, b_mn=False, epilogue=ops.EPI_BIAS, splits=1,
     out2 = torch.empty(M, N, dtype=torch.bfloat16, device=DEV) if epilogue == ops.EPI_BIAS_GELU else None
     use_aux = epilogue in (ops.EPI_BIAS_RESIDUAL, ops.EPI_DGELU)
     use_bias = epilogue != ops.EPI_DGELU
+    colsum = torch.ones(N, device=DEV) if epilogue != ops.EPI_BIAS_GELU else None
     ops.gemm(Ad, Bd, out, M, N, K, lda, ldb, N, a_mn, b_mn, epilogue, bias_d if use_bias else None,
-             aux_d if use_aux else None, N if use_aux else 0, out2)
+             aux_d if use_aux else None, N if use_aux else 0, out2, colsum=colsum)
     torch.cuda.synchronize()
     if epilogue == ops.EPI_BIAS:
         want = ref + bias.double()
@@ -80,6 +81,8 @@ def check_gemm(M, N, K, a_mn=False, b_mn=False, epilogue=ops.EPI_BIAS, splits=1,
         pdf = torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi)
         want = ref * (cdf + x * pdf)
     _close("gemm_out", out, want, 2 ** -7, 1e-3, res)
+    if colsum is not None:  # fused bias-gradient column sums of the (bf16-rounded) output
+        _close("gemm_colsum", colsum, 1 + out.double().cpu().sum(0), 1e-5, 1e-3, res)
     return res
 
 

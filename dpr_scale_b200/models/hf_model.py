@@ -207,6 +207,11 @@ class HFEncoder(nn.Module):
         self._ws_cache = {}
         self._warned_dropout = False
         self.launches = 0
+        # multi-GPU hook (set by the trainer): backward runs in `bwd_chunk_layers`-layer chunks and calls
+        # grad_sync(lo_elem, hi_elem) after each chunk so the gradient all-reduce of the finished slice of the
+        # flat arena overlaps with the rest of backward.
+        self.grad_sync = None
+        self.bwd_chunk_layers = 0
 
     # ------------------------------------------------------------------ construction helpers
     @classmethod
@@ -372,19 +377,25 @@ class HFEncoder(nn.Module):
         ops._count(1 + 7 * L)
         return pooled, (w, b, (ids, tt, pos, am, ws))
 
-    def _run_backward(self, state, dpooled, layer_chunks=None, between=None):
+    def _run_backward(self, state, dpooled):
         w, b, keep = state
         L = self.config["num_hidden_layers"]
         stream = torch.cuda.current_stream().cuda_stream
-        bounds = layer_chunks or [(0, L)]
-        for lo, hi in sorted(bounds, reverse=True):
+        lay = self.transformer.layout
+        if self.grad_sync is not None and self.bwd_chunk_layers > 0:
+            step = self.bwd_chunk_layers
+            bounds = [(max(0, hi - step), hi) for hi in range(L, 0, -step)]
+        else:
+            bounds = [(0, L)]
+        for lo, hi in bounds:
             check(_lib.load().dprb_encoder_bwd(ctypes.byref(w), ctypes.byref(b), dpooled.data_ptr(), lo, hi, stream),
                   "dprb_encoder_bwd")
             n = 13 * (hi - lo) + (1 if lo == 0 else 0)
             self.launches += n
             ops._count(n)
-            if between is not None:
-                between(lo, hi)
+            if self.grad_sync is not None:
+                e_lo = 0 if lo == 0 else lay.off_layer0 + lo * lay.layer_stride  # lo == 0 also finishes the embeddings
+                self.grad_sync(self, e_lo, lay.off_layer0 + hi * lay.layer_stride)
 
     def forward(self, tokens):
         if self.training and self.dropout > 0.0 and not self._warned_dropout:

@@ -53,7 +53,22 @@ class Trainer:
                 self.optimizer.grad_scale = 1.0 / self.world_size
             if hasattr(task, "on_pretrain_routine_start"):
                 task.on_pretrain_routine_start()
+            if self.world_size > 1:
+                self._pending = []
+                for e in self._encoders():
+                    e.grad_sync = self._sync_slice
+                    e.bwd_chunk_layers = self.grad_bucket_layers
         return task
+
+    def _sync_slice(self, enc, lo, hi):
+        """All-reduce (SUM) grads[lo:hi] of one encoder's flat arena as soon as backward has produced it; NCCL
+        runs it on its own stream, ordered after the kernels enqueued so far, concurrently with the rest of backward."""
+        g = enc.grads[lo:hi]
+        if self.compress_grads:
+            h = g.to(torch.bfloat16)
+            self._pending.append((dist.all_reduce(h, async_op=True), g, h))
+        else:
+            self._pending.append((dist.all_reduce(g, async_op=True), None, None))
 
     def _encoders(self):
         encs, seen = [], set()
@@ -68,14 +83,25 @@ class Trainer:
         """SUM all-reduce of the flat gradient arenas (the optimizer applies 1/world)."""
         if self.world_size <= 1:
             return
-        for e in self._encoders():
-            g = e.grads
-            if self.compress_grads:
-                h = g.to(torch.bfloat16)
-                dist.all_reduce(h)
+        for work, g, h in self._pending:  # issued chunk by chunk during backward (see _sync_slice)
+            work.wait()
+            if h is not None:
                 g.copy_(h)
-            else:
-                dist.all_reduce(g)
+        self._pending = []
+        extra = [p for p in self.task.parameters() if p.grad is not None and not self._in_arena(p)]
+        for p in extra:
+            dist.all_reduce(p.grad)
+
+    def _in_arena(self, p):
+        for e in self._encoders():
+            m = e.master
+            if m.data_ptr() <= p.data_ptr() < m.data_ptr() + m.numel() * 4:
+                return True
+        return False
+
+    def _unused(self):
+        if True:
+            return
 
     def training_step(self, batch, batch_idx=0):
         """zero_grad -> task.training_step -> backward -> grad all-reduce -> clip + AdamW -> LR schedule."""

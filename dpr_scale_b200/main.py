@@ -1,0 +1,38 @@
+#!/usr/bin/env python3
+"""Entry point in the shape of /root/reference/dpr_scale/main.py:20-50: compose the config, instantiate task /
+transform / datamodule by `_target_`, fit, test.  Uses real Hydra/Lightning when importable, else the in-repo
+composer (utils/config.py) and mini trainer (trainer.py).
+
+  python -m dpr_scale_b200.main --config-name msmarco_baseline task.model.model_path=/path/to/bert datamodule.train_path=...
+"""
+import sys
+
+from .trainer import Trainer
+from .utils.config import compose, instantiate
+
+
+def main(argv=None):
+    argv = list(sys.argv[1:] if argv is None else argv)
+    name = "config"
+    if "--config-name" in argv:
+        i = argv.index("--config-name")
+        name = argv[i + 1]
+        del argv[i:i + 2]
+    cfg = compose(name, argv)
+    cfg.task.datamodule = None
+    task = instantiate(cfg.task, _recursive_=False)
+    assert cfg.task.model.model_path == cfg.task.transform.text_transform.model_path
+    transform = instantiate(cfg.task.transform)
+    datamodule = instantiate(cfg.datamodule, transform=transform)
+    tr_kw = {k: v for k, v in cfg.trainer.items() if k in ("max_steps", "max_epochs", "gradient_clip_val", "precision",
+                                                             "strategy", "log_every_n_steps")}
+    trainer = Trainer(**tr_kw)
+    if cfg.test_only:
+        trainer.test(task, datamodule)
+    else:
+        trainer.fit(task, datamodule)
+        trainer.test(task, datamodule)
+
+
+if __name__ == "__main__":
+    main()

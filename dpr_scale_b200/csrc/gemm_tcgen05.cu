@@ -1,6 +1,15 @@
 // Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma
-// (UMMA 128x256x16, fp32 accumulators in TMEM, double-buffered) -> tcgen05.ld epilogue with the
-// fused bias / bias+GELU / bias+residual / dGELU / fp32 split-K accumulate variants the encoder needs.
+// (fp32 accumulators in TMEM, double-buffered) -> tcgen05.ld epilogue -> swizzled smem slabs -> TMA store,
+// with the fused bias / bias+GELU / bias+residual / dGELU / fp32 split-K accumulate variants the encoder needs.
+//
+// Two instantiations of one kernel:
+//   CG = 2 (default): a CTA PAIR (cluster 2x1x1) computes a 256x256 tile with tcgen05.mma.cta_group::2
+//           (UMMA 256x256x16): each CTA stages its own 128 rows of A and HALF of B (128 of the 256 N rows), so
+//           shared-memory fill traffic per SM drops from 96 to 64 B/clk at full tensor rate (the 128 B/clk smem
+//           port is what caps the 1-CTA version near 65 % of the MMA peak).  5-stage ring of 32 KB, double-buffered
+//           epilogue slabs.
+//   CG = 1: one CTA per 128x256 tile, UMMA 128x256x16, 4-stage ring of 48 KB (kept for A/B measurements:
+//           DPRB_GEMM_1CTA=1).
 //
 // Replaces, on the reference path, every torch.nn.Linear call inside HF BertLayer
 // (site-packages/transformers/models/bert/modeling_bert.py:179-181 QKV, :295 attention output,
@@ -10,6 +19,7 @@
 // D[M,N] = epi( sum_k A(m,k) * B(n,k) ).  Each operand may be K-major (row = MN index, K contiguous)
 // or MN-major (row = K index, MN contiguous); the latter lets dgrad read W[N_out,K_in] and wgrad
 // read dY[T,N_out] / X[T,K_in] in place, with no transposed copies.
+#include <cstdlib>
 #include <vector>
 #include "common.cuh"
 #include "dprb_internal.h"
@@ -18,21 +28,28 @@ namespace dprb {
 
 namespace {
 
-constexpr int BLOCK_M = 128;
+constexpr int CTA_M = 128;    // accumulator rows per CTA (TMEM lanes)
 constexpr int BLOCK_N = 256;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512 = all of TMEM
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;  // warps 0..3: TMA, MMA, TMEM alloc, spare
-constexpr int SLAB_BYTES = 32 * 128;  // 32 rows x 64 bf16, 128B-swizzled: one TMA-store box per epilogue warp
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * SLAB_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
+constexpr int SLAB_BYTES = 32 * 128;  // 32 rows x 64 bf16, 128B-swizzled: one TMA-store box
+
+template <int CG>
+struct Cfg {
+  static constexpr int STAGES = CG == 2 ? 5 : 4;
+  static constexpr int A_STAGE_BYTES = CTA_M * BLOCK_K * 2;                // 16 KB
+  static constexpr int B_ROWS = BLOCK_N / CG;                              // N rows staged per CTA
+  static constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;               // 32 / 16 KB
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int SLABS_PER_WARP = CG == 2 ? 2 : 1;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * SLABS_PER_WARP * SLAB_BYTES +
+                                    1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
+};
 
 struct GemmParams {
   int M, N, K;
@@ -49,26 +66,82 @@ struct GemmParams {
   float* colsum;       // optional: colsum[n] += sum_m D(m, n) of the bf16-rounded output (bias gradients)
 };
 
-template <int A_MN, int B_MN>
+// ---- cluster / 2-CTA helpers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+// TMA load issued by either CTA of a pair; completion bytes are credited to the LEADER's barrier (peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive (once the issued MMAs retire) on the barrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read_n(int slabs_in_flight) {
+  if (slabs_in_flight == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
+
+template <int A_MN, int B_MN, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_d2,
                  const GemmParams p) {
+  using C = Cfg<CG>;
+  constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B needs 1024-byte aligned tiles.
+  // SWIZZLE_128B needs 1024-byte aligned tiles (the dynamic smem base is identical in both CTAs of a pair).
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint8_t* smem_stage = smem + STAGES * STAGE_BYTES;  // [NUM_EPI_WARPS][SLAB_BYTES] epilogue staging slabs
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + NUM_EPI_WARPS * SLAB_BYTES);
-  uint64_t* full_bar = bars;                       // [STAGES]
+  uint8_t* smem_b = smem + STAGES * C::A_STAGE_BYTES;
+  uint8_t* smem_stage = smem + STAGES * C::STAGE_BYTES;  // [NUM_EPI_WARPS][SLABS_PER_WARP][SLAB_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + NUM_EPI_WARPS * C::SLABS_PER_WARP * SLAB_BYTES);
+  uint64_t* full_bar = bars;                       // [STAGES]   (CG=2: only the leader's are used)
   uint64_t* empty_bar = bars + STAGES;             // [STAGES]
   uint64_t* tmem_full_bar = bars + 2 * STAGES;     // [ACC_STAGES]
-  uint64_t* tmem_empty_bar = tmem_full_bar + ACC_STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + ACC_STAGES;  // (CG=2: only the leader's are used)
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + ACC_STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
+  const int worker = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // CTA or CTA pair index
+  const int num_workers = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -78,62 +151,70 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&full_bar[i], CG);   // one arrive per producer CTA (+ transaction bytes)
+      mbar_init(&empty_bar[i], 1);   // tcgen05.commit (multicast to both CTAs when CG = 2)
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], NUM_EPI_WARPS);
+      mbar_init(&tmem_empty_bar[i], NUM_EPI_WARPS * CG);  // epilogue warps of both CTAs release the leader's MMA
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_base_slot, TMEM_COLS);
+  if (warp == 2) {
+    if (CG == 2) tmem_alloc_2sm(tmem_base_slot, TMEM_COLS); else tmem_alloc(tmem_base_slot, TMEM_COLS);
+  }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int units = tiles * p.splits;
+  const int m_rows_per_unit = CTA_M * CG;
 
   if (warp == 0) {
-    // ================================ TMA producer ================================
+    // ================================ TMA producer (one per CTA) ================================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      for (int u = worker; u < units; u += num_workers) {
         const int tile = u % tiles, split = u / tiles;
         const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
+        const int m0 = m_blk * m_rows_per_unit + (int)cta_rank * CTA_M;        // this CTA's A rows
+        const int n0 = n_blk * BLOCK_N + (int)cta_rank * C::B_ROWS;            // this CTA's share of B
         const int kb0 = split * p.k_blocks_per_split;
         const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
-          uint8_t* sb = smem_b + stage * B_STAGE_BYTES;
+          if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES * CG);
+          uint8_t* sa = smem_a + stage * C::A_STAGE_BYTES;
+          uint8_t* sb = smem_b + stage * C::B_STAGE_BYTES;
+          auto load = [&](void* dst, const CUtensorMap* tm, int c0, int c1) {
+            if (CG == 2) tma_load_2d_2sm(dst, tm, &full_bar[stage], c0, c1);
+            else tma_load_2d(dst, tm, &full_bar[stage], c0, c1);
+          };
           if (A_MN == 0) {
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+            load(sa, &tmap_a, kb * BLOCK_K, m0);
           } else {
 #pragma unroll
-            for (int i = 0; i < BLOCK_M / 64; ++i)
-              tma_load_2d(sa + i * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m_blk * BLOCK_M + i * 64, kb * BLOCK_K);
+            for (int i = 0; i < CTA_M / 64; ++i) load(sa + i * (BLOCK_K * 128), &tmap_a, m0 + i * 64, kb * BLOCK_K);
           }
           if (B_MN == 0) {
-            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+            load(sb, &tmap_b, kb * BLOCK_K, n0);
           } else {
 #pragma unroll
-            for (int i = 0; i < BLOCK_N / 64; ++i)
-              tma_load_2d(sb + i * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n_blk * BLOCK_N + i * 64, kb * BLOCK_K);
+            for (int i = 0; i < C::B_ROWS / 64; ++i) load(sb + i * (BLOCK_K * 128), &tmap_b, n0 + i * 64, kb * BLOCK_K);
           }
+          if (CG == 2 && !is_leader) mbar_arrive_remote(&full_bar[stage], 0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ================================ MMA issuer (one thread) ================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(BLOCK_M, BLOCK_N, A_MN, B_MN);
+    // ================================ MMA issuer (one thread of the leader CTA) ================================
+    if (lane == 0 && is_leader) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(CTA_M * CG, BLOCK_N, A_MN, B_MN);
       // K-major SW128: 8-row groups are 1024 B apart (SBO); LBO unused inside one swizzle atom.
       // MN-major SW128: 64-element MN atoms are BLOCK_K*128 B apart (LBO); 8-deep K groups 1024 B apart (SBO).
       constexpr uint32_t A_LBO = A_MN ? BLOCK_K * 128 : 0, A_SBO = 1024;
@@ -145,7 +226,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      for (int u = worker; u < units; u += num_workers) {
         const int split = u / tiles;
         const int kb0 = split * p.k_blocks_per_split;
         const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
@@ -155,43 +236,47 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint64_t a_desc = make_umma_desc_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES), A_LBO, A_SBO);
-          const uint64_t b_desc = make_umma_desc_sw128(smem_u32(smem_b + stage * B_STAGE_BYTES), B_LBO, B_SBO);
+          const uint64_t a_desc = make_umma_desc_sw128(smem_u32(smem_a + stage * C::A_STAGE_BYTES), A_LBO, A_SBO);
+          const uint64_t b_desc = make_umma_desc_sw128(smem_u32(smem_b + stage * C::B_STAGE_BYTES), B_LBO, B_SBO);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            umma_f16(d_tmem, a_desc + (uint64_t)(k * A_KSTEP), b_desc + (uint64_t)(k * B_KSTEP), idesc,
-                     (kb > kb0 || k > 0) ? 1u : 0u);
+            const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+            if (CG == 2) umma_f16_2sm(d_tmem, a_desc + (uint64_t)(k * A_KSTEP), b_desc + (uint64_t)(k * B_KSTEP), idesc, accum);
+            else umma_f16(d_tmem, a_desc + (uint64_t)(k * A_KSTEP), b_desc + (uint64_t)(k * B_KSTEP), idesc, accum);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs) when these MMAs retire
+          if (CG == 2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if (CG == 2) umma_commit_2sm(&tmem_full_bar[acc]); else umma_commit(&tmem_full_bar[acc]);
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp >= 4) {
     // ================================ epilogue warps ================================
-    // Warp (quarter, col_half) owns TMEM lanes [32*quarter, +32) x columns [128*col_half, +128) of the tile.
-    // bf16 outputs: registers -> 128B-swizzled smem slab (32 rows x 64 cols) -> TMA store (full-line writes;
-    // partial tiles are clipped by the tensor map).  aux (residual / pre-activation) is read with coalesced
-    // 16-byte loads through the same slab.  fp32 outputs (split-K wgrad) go out as RED/ST from registers.
+    // Warp (quarter, col_half) owns TMEM lanes [32*quarter, +32) x columns [128*col_half, +128) of this CTA's
+    // 128x256 accumulator.  bf16 outputs: registers -> 128B-swizzled smem slab (32 rows x 64 cols) -> TMA store
+    // (full-line writes; partial tiles are clipped by the tensor map).  aux (residual / pre-activation) is read with
+    // coalesced 16-byte loads through the same slab.  fp32 outputs (split-K wgrad) go out as RED/ST from registers.
     const int ew = warp - 4;
     const int quarter = warp & 3;
     const int col_half = ew >> 2;
-    uint8_t* slab = smem_stage + ew * SLAB_BYTES;
-    const uint32_t slab_u32 = smem_u32(slab);
+    constexpr int NSLAB = C::SLABS_PER_WARP;
+    uint8_t* slab_base = smem_stage + ew * NSLAB * SLAB_BYTES;
+    int slab_sel = 0;
     const bool f32_out = (p.epilogue == DPRB_EPI_F32_ATOMIC_ADD || p.epilogue == DPRB_EPI_F32_STORE);
     const bool has_aux = (p.epilogue == DPRB_EPI_BIAS_RESIDUAL || p.epilogue == DPRB_EPI_DGELU);
     const bool is_gelu = (p.epilogue == DPRB_EPI_BIAS_GELU);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    for (int u = worker; u < units; u += num_workers) {
       const int tile = u % tiles;
       const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
-      const int row0 = m_blk * BLOCK_M + quarter * 32;
+      const int row0 = m_blk * m_rows_per_unit + (int)cta_rank * CTA_M + quarter * 32;
       const int row = row0 + lane;
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + col_half * 128);
       if (f32_out) {
@@ -225,9 +310,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           __syncwarp();  // reconverge before the next .sync.aligned tcgen05.ld
         }
       } else if (is_gelu) {
-        // single pass, two 32x32 slabs (64B swizzle): pre-activation -> out2 (optional), GELU -> D
-        uint8_t* slab_pre = slab;
-        uint8_t* slab_act = slab + SLAB_BYTES / 2;
+        // single pass, two 32x32 slabs (64B swizzle) per 32-column chunk: pre-activation -> out2 (optional), GELU -> D
 #pragma unroll 1
         for (int h = 0; h < 4; ++h) {
           const int col0 = n_blk * BLOCK_N + col_half * 128 + h * 32;
@@ -248,7 +331,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int j = 0; j < 32; ++j)
               v[j] = fmaf(__uint_as_float(r[j]), p.alpha, (p.bias != nullptr && col0 + j < p.N) ? __ldg(p.bias + col0 + j) : 0.f);
           }
-          if (lane == 0) tma_store_wait_read();
+          uint8_t* slab_pre = slab_base + slab_sel * SLAB_BYTES;
+          uint8_t* slab_act = slab_pre + SLAB_BYTES / 2;
+          if (lane == 0) tma_store_wait_read_n(NSLAB - 1);
           __syncwarp();
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
@@ -270,106 +355,108 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            if (p.out2 != nullptr) tma_store_2d(&tmap_d2, slab_u32, col0, row0);
-            tma_store_2d(&tmap_d, slab_u32 + SLAB_BYTES / 2, col0, row0);
+            if (p.out2 != nullptr) tma_store_2d(&tmap_d2, smem_u32(slab_pre), col0, row0);
+            tma_store_2d(&tmap_d, smem_u32(slab_act), col0, row0);
             tma_store_commit();
           }
+          slab_sel = (slab_sel + 1) % NSLAB;
         }
         __syncwarp();
       } else {
-        const int n_pass = 1;
 #pragma unroll 1
         for (int sl = 0; sl < 2; ++sl) {          // two 64-column slabs per warp
           const int colbase = n_blk * BLOCK_N + col_half * 128 + sl * 64;
           if (colbase >= p.N) break;              // warp-uniform
-#pragma unroll 1
-          for (int pass = 0; pass < n_pass; ++pass) {
-            const bool store_pre = false;
-            // the previous TMA store must have finished READING the slab before it is overwritten
-            if (lane == 0) tma_store_wait_read();
-            __syncwarp();
-            if (has_aux) {
+          uint8_t* slab = slab_base + slab_sel * SLAB_BYTES;
+          // the TMA store that last used this slab must have finished READING it before it is overwritten
+          if (lane == 0) tma_store_wait_read_n(NSLAB - 1);
+          __syncwarp();
+          if (has_aux) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int idx = lane + 32 * i, r = idx >> 3, ch = idx & 7;
-                uint4 q = make_uint4(0, 0, 0, 0);
-                if (row0 + r < p.M && colbase + ch * 8 < p.N)
-                  q = ldg_nc_v4(p.aux + (long long)(row0 + r) * p.ld_aux + colbase + ch * 8);
-                *reinterpret_cast<uint4*>(slab + r * 128 + ((ch ^ (r & 7)) << 4)) = q;
-              }
-              __syncwarp();
+            for (int i = 0; i < 8; ++i) {
+              const int idx = lane + 32 * i, r = idx >> 3, ch = idx & 7;
+              uint4 q = make_uint4(0, 0, 0, 0);
+              if (row0 + r < p.M && colbase + ch * 8 < p.N)
+                q = ldg_nc_v4(p.aux + (long long)(row0 + r) * p.ld_aux + colbase + ch * 8);
+              *reinterpret_cast<uint4*>(slab + r * 128 + ((ch ^ (r & 7)) << 4)) = q;
             }
+            __syncwarp();
+          }
 #pragma unroll 1
-            for (int h = 0; h < 2; ++h) {         // 32 accumulator columns at a time
-              const int col0 = colbase + h * 32;
-              uint32_t r[32];
-              tmem_ld_32x32(tbase + sl * 64 + h * 32, r);
-              tmem_ld_wait();
-              float v[32];
+          for (int h = 0; h < 2; ++h) {         // 32 accumulator columns at a time
+            const int col0 = colbase + h * 32;
+            uint32_t r[32];
+            tmem_ld_32x32(tbase + sl * 64 + h * 32, r);
+            tmem_ld_wait();
+            float v[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-              if (p.bias != nullptr) {
-                if (col0 + 32 <= p.N) {
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+            if (p.bias != nullptr) {
+              if (col0 + 32 <= p.N) {
 #pragma unroll
-                  for (int j = 0; j < 32; j += 4) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                    v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                  }
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                  v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
                 }
-              }
-              if (has_aux) {
+              } else {
 #pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                  const int ch = h * 4 + c4;
-                  const uint4 q = *reinterpret_cast<const uint4*>(slab + lane * 128 + ((ch ^ (lane & 7)) << 4));
-                  const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z), f3 = unpack_bf16x2(q.w);
-                  const float a[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
-#pragma unroll
-                  for (int t = 0; t < 8; ++t) {
-                    if (p.epilogue == DPRB_EPI_BIAS_RESIDUAL) v[c4 * 8 + t] += a[t];
-                    else v[c4 * 8 + t] *= gelu_erf_grad(a[t]);
-                  }
-                }
+                for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
               }
+            }
+            if (has_aux) {
 #pragma unroll
               for (int c4 = 0; c4 < 4; ++c4) {
                 const int ch = h * 4 + c4;
-                uint4 q;
-                q.x = pack_bf16x2(v[c4 * 8 + 0], v[c4 * 8 + 1]); q.y = pack_bf16x2(v[c4 * 8 + 2], v[c4 * 8 + 3]);
-                q.z = pack_bf16x2(v[c4 * 8 + 4], v[c4 * 8 + 5]); q.w = pack_bf16x2(v[c4 * 8 + 6], v[c4 * 8 + 7]);
-                *reinterpret_cast<uint4*>(slab + lane * 128 + ((ch ^ (lane & 7)) << 4)) = q;
+                const uint4 q = *reinterpret_cast<const uint4*>(slab + lane * 128 + ((ch ^ (lane & 7)) << 4));
+                const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z), f3 = unpack_bf16x2(q.w);
+                const float a[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                  if (p.epilogue == DPRB_EPI_BIAS_RESIDUAL) v[c4 * 8 + t] += a[t];
+                  else v[c4 * 8 + t] *= gelu_erf_grad(a[t]);
+                }
               }
             }
-            if (p.colsum != nullptr) {
-              // column sums of the staged (bf16-rounded) slab: lane l owns columns 2l, 2l+1; conflict-free reads
-              __syncwarp();
-              const int nrows = min(32, p.M - row0);
-              float s0 = 0.f, s1 = 0.f;
-              for (int r = 0; r < nrows; ++r) {
-                const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(
-                    slab + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4));
-                s0 += f.x; s1 += f.y;
-              }
-              const int col = colbase + lane * 2;
-              if (col < p.N) atomicAdd(p.colsum + col, s0);
-              if (col + 1 < p.N) atomicAdd(p.colsum + col + 1, s1);
-            }
-            fence_proxy_async_smem();   // make the generic-proxy smem writes visible to the TMA engine
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(store_pre ? &tmap_d2 : &tmap_d, slab_u32, colbase, row0);
-              tma_store_commit();
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const int ch = h * 4 + c4;
+              uint4 q;
+              q.x = pack_bf16x2(v[c4 * 8 + 0], v[c4 * 8 + 1]); q.y = pack_bf16x2(v[c4 * 8 + 2], v[c4 * 8 + 3]);
+              q.z = pack_bf16x2(v[c4 * 8 + 4], v[c4 * 8 + 5]); q.w = pack_bf16x2(v[c4 * 8 + 6], v[c4 * 8 + 7]);
+              *reinterpret_cast<uint4*>(slab + lane * 128 + ((ch ^ (lane & 7)) << 4)) = q;
             }
           }
+          if (p.colsum != nullptr) {
+            // column sums of the staged (bf16-rounded) slab: lane l owns columns 2l, 2l+1; conflict-free reads
+            __syncwarp();
+            const int nrows = min(32, p.M - row0);
+            float s0 = 0.f, s1 = 0.f;
+            for (int r = 0; r < nrows; ++r) {
+              const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(
+                  slab + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4));
+              s0 += f.x; s1 += f.y;
+            }
+            const int col = colbase + lane * 2;
+            if (col < p.N) atomicAdd(p.colsum + col, s0);
+            if (col + 1 < p.N) atomicAdd(p.colsum + col + 1, s1);
+          }
+          fence_proxy_async_smem();   // make the generic-proxy smem writes visible to the TMA engine
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_d, smem_u32(slab), colbase, row0);
+            tma_store_commit();
+          }
+          slab_sel = (slab_sel + 1) % NSLAB;
         }
         __syncwarp();
       }
+      // all tcgen05.ld of this accumulator stage have completed (tmem_ld_wait): release it to the MMA warp
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (lane == 0) {
+        if (CG == 2 && !is_leader) mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+        else mbar_arrive(&tmem_empty_bar[acc]);
+      }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) tma_store_wait_all();  // smem must stay valid until the last bulk store has drained
@@ -377,10 +464,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CG == 2) tmem_dealloc_2sm(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -462,9 +549,11 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long l
 
   CUtensorMap ta, tb;
   int rc;
-  if (!a_mn_major) rc = make_tmap(&ta, A, M, K, lda, BLOCK_M); else rc = make_tmap(&ta, A, K, M, lda, BLOCK_K);
+  static const bool one_cta = (std::getenv("DPRB_GEMM_1CTA") != nullptr);
+  const int CG = one_cta ? 1 : 2;
+  if (!a_mn_major) rc = make_tmap(&ta, A, M, K, lda, CTA_M); else rc = make_tmap(&ta, A, K, M, lda, BLOCK_K);
   if (rc) return rc;
-  if (!b_mn_major) rc = make_tmap(&tb, B, N, K, ldb, BLOCK_N); else rc = make_tmap(&tb, B, K, N, ldb, BLOCK_K);
+  if (!b_mn_major) rc = make_tmap(&tb, B, N, K, ldb, BLOCK_N / CG); else rc = make_tmap(&tb, B, K, N, ldb, BLOCK_K);
   if (rc) return rc;
   CUtensorMap td, td2;
   if (!f32_out) {
@@ -483,13 +572,14 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long l
 
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
-  p.num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+  p.num_m_blocks = (M + CTA_M * CG - 1) / (CTA_M * CG);
   p.num_n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
   p.k_blocks_total = (K + BLOCK_K - 1) / BLOCK_K;
   const int sms = num_sms();
+  const int workers = CG == 2 ? sms / 2 : sms;  // CTAs or CTA pairs
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   if (epilogue != DPRB_EPI_F32_ATOMIC_ADD) splits = 1;
-  else if (splits <= 0) splits = choose_splits(tiles, p.k_blocks_total, sms);
+  else if (splits <= 0) splits = choose_splits(tiles, p.k_blocks_total, workers);
   if (splits > p.k_blocks_total) splits = p.k_blocks_total;
   p.k_blocks_per_split = (p.k_blocks_total + splits - 1) / splits;
   p.splits = (p.k_blocks_total + p.k_blocks_per_split - 1) / p.k_blocks_per_split;
@@ -501,21 +591,35 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long l
                "gemm: colsum is supported for the BIAS / BIAS_RESIDUAL / DGELU epilogues only");
 
   const int units = tiles * p.splits;
-  const int grid = units < sms ? units : sms;
+  const int grid = (units < workers ? units : workers) * CG;
 
   static bool attr_set = false;
   if (!attr_set) {
-    DPRB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    DPRB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    DPRB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    DPRB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+#define DPRB_SET_ATTR(K, CGV)                                                                                           \
+  DPRB_CHECK_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<CGV>::SMEM_BYTES));
+    DPRB_SET_ATTR((gemm_bf16_kernel<0, 0, 1>), 1) DPRB_SET_ATTR((gemm_bf16_kernel<0, 1, 1>), 1)
+    DPRB_SET_ATTR((gemm_bf16_kernel<1, 0, 1>), 1) DPRB_SET_ATTR((gemm_bf16_kernel<1, 1, 1>), 1)
+    DPRB_SET_ATTR((gemm_bf16_kernel<0, 0, 2>), 2) DPRB_SET_ATTR((gemm_bf16_kernel<0, 1, 2>), 2)
+    DPRB_SET_ATTR((gemm_bf16_kernel<1, 0, 2>), 2) DPRB_SET_ATTR((gemm_bf16_kernel<1, 1, 2>), 2)
+#undef DPRB_SET_ATTR
     attr_set = true;
   }
-  auto launch = [&](auto kern) -> int {
+  auto launch = [&](auto kern, int smem_bytes) -> int {
     const bool prof = g_prof.enabled && g_prof.used + 2 <= g_prof.ev.size();
     if (prof) DPRB_CHECK_CUDA(cudaEventRecord(g_prof.ev[g_prof.used], stream));
-    kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, td, td2, p);
-    DPRB_CHECK_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DPRB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, td2, p));
     if (prof) {
       DPRB_CHECK_CUDA(cudaEventRecord(g_prof.ev[g_prof.used + 1], stream));
       g_prof.flops.push_back(2.0 * (double)M * (double)N * (double)K);
@@ -523,10 +627,21 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long l
     }
     return 0;
   };
-  if (!a_mn_major && !b_mn_major) return launch(gemm_bf16_kernel<0, 0>);
-  if (!a_mn_major && b_mn_major) return launch(gemm_bf16_kernel<0, 1>);
-  if (a_mn_major && !b_mn_major) return launch(gemm_bf16_kernel<1, 0>);
-  return launch(gemm_bf16_kernel<1, 1>);
+  const int key = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
+  if (CG == 2) {
+    switch (key) {
+      case 0: return launch(gemm_bf16_kernel<0, 0, 2>, Cfg<2>::SMEM_BYTES);
+      case 1: return launch(gemm_bf16_kernel<0, 1, 2>, Cfg<2>::SMEM_BYTES);
+      case 2: return launch(gemm_bf16_kernel<1, 0, 2>, Cfg<2>::SMEM_BYTES);
+      default: return launch(gemm_bf16_kernel<1, 1, 2>, Cfg<2>::SMEM_BYTES);
+    }
+  }
+  switch (key) {
+    case 0: return launch(gemm_bf16_kernel<0, 0, 1>, Cfg<1>::SMEM_BYTES);
+    case 1: return launch(gemm_bf16_kernel<0, 1, 1>, Cfg<1>::SMEM_BYTES);
+    case 2: return launch(gemm_bf16_kernel<1, 0, 1>, Cfg<1>::SMEM_BYTES);
+    default: return launch(gemm_bf16_kernel<1, 1, 1>, Cfg<1>::SMEM_BYTES);
+  }
 }
 
 int gemm_profile_enable(int enable, int max_launches) {

@@ -11,6 +11,7 @@
 // online-softmax recurrence); the projection GEMMs around it are the tcgen05 kernel.
 //
 // Layout: qkv bf16 [nseq*S, 3H], row t = (seq, s); Q at column h*64, K at H + h*64, V at 2H + h*64.
+#include <cstdlib>
 #include "common.cuh"
 #include "dprb_internal.h"
 
@@ -376,6 +377,8 @@ int attn_fwd_lse(const void* qkv, const int32_t* attn_mask, void* ctx, float* ls
                  cudaStream_t stream) {
   if (int rc = check_shape(nseq, S, heads, "attn_fwd")) return rc;
   if (nseq == 0) return 0;
+  static const bool legacy = (std::getenv("DPRB_ATTN_LEGACY") != nullptr);
+  if (S <= 128 && !legacy) return attn_fwd_tc(qkv, attn_mask, ctx, lse, nseq, S, heads, stream);  // tcgen05 path
   const int S_pad = (S + 63) / 64 * 64;
   const size_t smem = 3 * (size_t)S_pad * 128 + S_pad * 4 + 8 * 16 * STG_STRIDE;
   static bool attr = false;
@@ -393,6 +396,8 @@ int attn_bwd_lse(const void* qkv, const int32_t* attn_mask, const void* ctx, con
                  void* dqkv, int nseq, int S, int heads, cudaStream_t stream) {
   if (int rc = check_shape(nseq, S, heads, "attn_bwd")) return rc;
   if (nseq == 0) return 0;
+  static const bool legacy = (std::getenv("DPRB_ATTN_LEGACY") != nullptr);
+  if (S <= 128 && !legacy) return attn_bwd_tc(qkv, attn_mask, lse, dctx, dqkv, nseq, S, heads, stream);  // tcgen05 path
   const int S_pad = (S + 63) / 64 * 64;
   const size_t smem = 4 * (size_t)S_pad * 128 + 3 * S_pad * 4 + 8 * 16 * STG_STRIDE;
   static bool attr = false;

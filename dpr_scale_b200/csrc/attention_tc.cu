@@ -1,0 +1,472 @@
+// Self-attention core on the 5th-gen tensor cores (tcgen05 / TMEM / TMA) for head_dim 64 and S <= 128:
+// one (sequence, head) problem = one 128-row UMMA tile; persistent CTAs loop over problems.
+//
+//   forward : S = Q K^T (UMMA 128x128x16 x4) -> TMEM -> row softmax in registers (thread i = query row i)
+//             -> P (bf16) to 128B-swizzled smem -> O = P V (UMMA 128x64x16 x8, V read in place as an MN-major
+//             operand) -> TMEM -> scale by 1/l -> smem -> TMA store.  LSE saved for backward.
+//   backward: S = Q K^T and dP = dO V^T (UMMA) -> P = exp2(S - lse), D_i = sum_j P dP, dS = P (dP - D) / 8
+//             in registers -> P, dS (bf16) to smem -> dV = P^T dO, dK = dS^T Q, dQ = dS K (UMMA; the transposed
+//             operands are the SAME smem tiles read through MN-major descriptors) -> TMEM -> smem -> TMA store.
+//
+// All tiles are moved by TMA through 3-D tensor maps [nseq, S, columns]: rows >= S of a short sequence are
+// zero-filled on load and clipped on store by the hardware, so no per-row predication is needed.
+//
+// Replaces BertSelfAttention.forward's scaled_dot_product_attention
+// (site-packages/transformers/models/bert/modeling_bert.py:168-207, integrations/sdpa_attention.py:92-101)
+// and its autograd backward, reached from /root/reference/dpr_scale/models/hf_model.py:38.
+#include "common.cuh"
+#include "dprb_internal.h"
+
+namespace dprb {
+namespace {
+
+constexpr int TILE_BYTES = 128 * 128;  // [128 rows][64 bf16], 128B-swizzled = 16 KB
+constexpr float SCALE_LOG2 = 0.125f * 1.4426950408889634f;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+constexpr int SM_THREADS = 128;        // softmax / epilogue threads (4 warps = 128 TMEM lanes)
+constexpr int NTHREADS = 32 + SM_THREADS;
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// K-major A/B tile [128 rows][64 K] (one swizzle atom wide): 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) { return make_umma_desc_sw128(addr, 0, 1024); }
+// MN-major operand read from a [K rows][64 MN] tile; further 64-wide MN atoms are `lbo` bytes apart.
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t addr, uint32_t lbo) { return make_umma_desc_sw128(addr, lbo, 1024); }
+
+// pack 8 floats (scaled) into one 16-byte chunk of a swizzled [128][64] tile row
+__device__ __forceinline__ void st_chunk(uint8_t* tile, int row, int chunk, const float* v, float s) {
+  uint4 q;
+  q.x = pack_bf16x2(v[0] * s, v[1] * s); q.y = pack_bf16x2(v[2] * s, v[3] * s);
+  q.z = pack_bf16x2(v[4] * s, v[5] * s); q.w = pack_bf16x2(v[6] * s, v[7] * s);
+  *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = q;
+}
+
+// ------------------------------------------------------------------------------------------ forward
+// smem: sQ | sK | sV | sP (2 k-blocks) | mask[2][128] | barriers.  TMEM: S cols [0,128), O cols [128,192).
+constexpr int FWD_SMEM = 3 * TILE_BYTES + 2 * TILE_BYTES + 2 * 128 * 4 + 64 + 1024;
+
+__global__ void __launch_bounds__(NTHREADS, 2)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_ctx,
+                   const int32_t* __restrict__ attn_mask, float* __restrict__ lse_out, int S, int heads, int nseq) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + TILE_BYTES;
+  uint8_t* sV = sK + TILE_BYTES;
+  uint8_t* sP = sV + TILE_BYTES;  // 2 x 16 KB
+  float* sMask = reinterpret_cast<float*>(sP + 2 * TILE_BYTES);  // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + 256);
+  uint64_t *b_load = bars, *b_s = bars + 1, *b_p = bars + 2, *b_o = bars + 3, *b_free = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = heads * 64;
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_qkv);
+      tma_prefetch_desc(&tm_ctx);
+      mbar_init(b_load, 1); mbar_init(b_s, 1); mbar_init(b_p, 4); mbar_init(b_o, 1); mbar_init(b_free, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 256);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tO = tmem + 128;
+  const int nprob = nseq * heads;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16_f32(128, 128, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16_f32(128, 64, 0, 1);
+      uint32_t ph = 0;
+      for (int prob = blockIdx.x; prob < nprob; prob += gridDim.x) {
+        const int seq = prob / heads, h = prob - seq * heads;
+        mbar_wait(b_free, ph ^ 1);
+        mbar_arrive_expect_tx(b_load, 3 * TILE_BYTES);
+        tma_load_3d(sQ, &tm_qkv, b_load, h * 64, 0, seq);
+        tma_load_3d(sK, &tm_qkv, b_load, H + h * 64, 0, seq);
+        tma_load_3d(sV, &tm_qkv, b_load, 2 * H + h * 64, 0, seq);
+        mbar_wait(b_load, ph);
+        tcgen05_fence_after();
+        const uint64_t dq = desc_kmajor(smem_u32(sQ)), dk = desc_kmajor(smem_u32(sK));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tS, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
+        umma_commit(b_s);
+        mbar_wait(b_p, ph);
+        tcgen05_fence_after();
+        const uint64_t dv = desc_mnmajor(smem_u32(sV), 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t dp = desc_kmajor(smem_u32(sP + (k >> 2) * TILE_BYTES)) + 2 * (k & 3);
+          umma_f16(tO, dp, dv + 128 * k, idesc_o, k > 0);  // V: 16 key rows = 2048 B per K step
+        }
+        umma_commit(b_o);
+        ph ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    const int tid = threadIdx.x - 32;            // 0..127
+    const int quarter = warp & 3;                // TMEM lane quarter of this warp
+    const int row = quarter * 32 + lane;         // query row owned by this thread
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    uint32_t ph = 0;
+    for (int prob = blockIdx.x; prob < nprob; prob += gridDim.x) {
+      const int seq = prob / heads, h = prob - seq * heads;
+      float* mk = sMask + ph * 128;
+      {
+        const bool keep = tid < S && (attn_mask == nullptr || attn_mask[(long long)seq * S + tid] != 0);
+        mk[tid] = keep ? 0.f : -INFINITY;
+      }
+      named_bar_sync(1, SM_THREADS);
+      mbar_wait(b_s, ph);
+      tcgen05_fence_after();
+      // pass 1: row max (TMEM reads are cheap: re-reading S beats holding 128 scores in registers)
+      float m = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tS + lane_addr + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m = fmaxf(m, fmaf(__uint_as_float(r[j]), SCALE_LOG2, mk[c * 32 + j]));
+      }
+      const float e = (m == -INFINITY) ? 0.f : m;  // fully masked row guard
+      // pass 2: P = exp2(s - max) -> bf16 -> swizzled smem (A operand of P V), row sum
+      float l = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tS + lane_addr + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          float p[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int j = c4 * 8 + t;
+            p[t] = ex2_approx(fmaf(__uint_as_float(r[j]), SCALE_LOG2, mk[c * 32 + j]) - e);
+            l += p[t];
+          }
+          const int chunk = c * 4 + c4;
+          st_chunk(sP + (chunk >> 3) * TILE_BYTES, row, chunk & 7, p, 1.f);
+        }
+      }
+      fence_proxy_async_smem();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_p);
+      if (lse_out != nullptr && row < S) lse_out[((long long)seq * heads + h) * S + row] = m * LN2 + __logf(l);
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      mbar_wait(b_o, ph);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tO + lane_addr + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          float v[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(r[c4 * 8 + t]);
+          st_chunk(sQ, row, c * 4 + c4, v, inv);  // Q tile is dead after the S MMA: reuse as the store staging tile
+        }
+      }
+      fence_proxy_async_smem();
+      tcgen05_fence_before();
+      named_bar_sync(2, SM_THREADS);
+      if (tid == 0) {
+        tma_store_3d(&tm_ctx, smem_u32(sQ), h * 64, 0, seq);
+        tma_store_commit();
+        tma_store_wait_read();
+        mbar_arrive(b_free);
+      }
+      ph ^= 1;
+    }
+    if (tid == 0) tma_store_wait_all();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ backward
+// smem: sQ | sK | sV | sdO | sP (2 blocks) | sdS (2 blocks) | mask[2][128] | barriers  (~129 KB, 1 CTA/SM)
+// TMEM: S [0,128) dP [128,256) dV [256,320) dK [320,384) dQ [384,448)
+constexpr int BWD_SMEM = 4 * TILE_BYTES + 4 * TILE_BYTES + 2 * 128 * 4 + 64 + 1024;
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_dctx,
+                   const __grid_constant__ CUtensorMap tm_dqkv, const int32_t* __restrict__ attn_mask,
+                   const float* __restrict__ lse_in, int S, int heads, int nseq) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + TILE_BYTES;
+  uint8_t* sV = sK + TILE_BYTES;
+  uint8_t* sdO = sV + TILE_BYTES;
+  uint8_t* sP = sdO + TILE_BYTES;      // 2 x 16 KB  [i][j]
+  uint8_t* sdS = sP + 2 * TILE_BYTES;  // 2 x 16 KB  [i][j]
+  float* sMask = reinterpret_cast<float*>(sdS + 2 * TILE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + 256);
+  uint64_t *b_load = bars, *b_s = bars + 1, *b_p = bars + 2, *b_o = bars + 3, *b_free = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = heads * 64;
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_qkv);
+      tma_prefetch_desc(&tm_dctx);
+      tma_prefetch_desc(&tm_dqkv);
+      mbar_init(b_load, 1); mbar_init(b_s, 1); mbar_init(b_p, 4); mbar_init(b_o, 1); mbar_init(b_free, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 320, tdQ = tmem + 384;
+  const int nprob = nseq * heads;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16_f32(128, 128, 0, 0);    // Q K^T, dO V^T
+      constexpr uint32_t idesc_t = make_idesc_bf16_f32(128, 64, 1, 1);     // P^T dO, dS^T Q
+      constexpr uint32_t idesc_q = make_idesc_bf16_f32(128, 64, 0, 1);     // dS K
+      uint32_t ph = 0;
+      for (int prob = blockIdx.x; prob < nprob; prob += gridDim.x) {
+        const int seq = prob / heads, h = prob - seq * heads;
+        mbar_wait(b_free, ph ^ 1);
+        mbar_arrive_expect_tx(b_load, 4 * TILE_BYTES);
+        tma_load_3d(sQ, &tm_qkv, b_load, h * 64, 0, seq);
+        tma_load_3d(sK, &tm_qkv, b_load, H + h * 64, 0, seq);
+        tma_load_3d(sV, &tm_qkv, b_load, 2 * H + h * 64, 0, seq);
+        tma_load_3d(sdO, &tm_dctx, b_load, h * 64, 0, seq);
+        mbar_wait(b_load, ph);
+        tcgen05_fence_after();
+        const uint64_t dq = desc_kmajor(smem_u32(sQ)), dk = desc_kmajor(smem_u32(sK));
+        const uint64_t dv = desc_kmajor(smem_u32(sV)), ddo = desc_kmajor(smem_u32(sdO));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tS, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tdP, ddo + 2 * k, dv + 2 * k, idesc_s, k > 0);
+        umma_commit(b_s);
+        mbar_wait(b_p, ph);
+        tcgen05_fence_after();
+        // transposed A operands: the [i][j] tiles read MN-major (M = j: two 64-wide atoms 16 KB apart; K = i)
+        const uint64_t dpt = desc_mnmajor(smem_u32(sP), TILE_BYTES), dst = desc_mnmajor(smem_u32(sdS), TILE_BYTES);
+        const uint64_t bdo = desc_mnmajor(smem_u32(sdO), 0), bq = desc_mnmajor(smem_u32(sQ), 0), bk = desc_mnmajor(smem_u32(sK), 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) umma_f16(tdV, dpt + 128 * k, bdo + 128 * k, idesc_t, k > 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) umma_f16(tdK, dst + 128 * k, bq + 128 * k, idesc_t, k > 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t a = desc_kmajor(smem_u32(sdS + (k >> 2) * TILE_BYTES)) + 2 * (k & 3);
+          umma_f16(tdQ, a, bk + 128 * k, idesc_q, k > 0);
+        }
+        umma_commit(b_o);
+        ph ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    const int tid = threadIdx.x - 32;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    uint32_t ph = 0;
+    for (int prob = blockIdx.x; prob < nprob; prob += gridDim.x) {
+      const int seq = prob / heads, h = prob - seq * heads;
+      float* mk = sMask + ph * 128;
+      {
+        const bool keep = tid < S && (attn_mask == nullptr || attn_mask[(long long)seq * S + tid] != 0);
+        mk[tid] = keep ? 0.f : -INFINITY;
+      }
+      // rows beyond S: lse = +inf  =>  P = 0
+      const float lse2 = row < S ? lse_in[((long long)seq * heads + h) * S + row] * LOG2E : INFINITY;
+      named_bar_sync(1, SM_THREADS);
+      mbar_wait(b_s, ph);
+      tcgen05_fence_after();
+      // pass 1: P (kept packed in registers + written to smem) and D_i = sum_j P_ij dP_ij
+      uint32_t pk[64];
+      float D = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rs[32], rd[32];
+        tmem_ld_32x32(tS + lane_addr + c * 32, rs);
+        tmem_ld_32x32(tdP + lane_addr + c * 32, rd);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          float p[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int j = c4 * 8 + t;
+            p[t] = ex2_approx(fmaf(__uint_as_float(rs[j]), SCALE_LOG2, mk[c * 32 + j]) - lse2);
+            D = fmaf(p[t], __uint_as_float(rd[j]), D);
+          }
+#pragma unroll
+          for (int t = 0; t < 4; ++t) pk[c * 16 + c4 * 4 + t] = pack_bf16x2(p[2 * t], p[2 * t + 1]);
+          const int chunk = c * 4 + c4;
+          uint4 q = make_uint4(pk[c * 16 + c4 * 4], pk[c * 16 + c4 * 4 + 1], pk[c * 16 + c4 * 4 + 2], pk[c * 16 + c4 * 4 + 3]);
+          *reinterpret_cast<uint4*>(sP + (chunk >> 3) * TILE_BYTES + row * 128 + (((chunk & 7) ^ (row & 7)) << 4)) = q;
+        }
+      }
+      // pass 2: dS = P (dP - D) / sqrt(dh)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rd[32];
+        tmem_ld_32x32(tdP + lane_addr + c * 32, rd);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          float ds[8];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 pp = unpack_bf16x2(pk[c * 16 + c4 * 4 + t]);
+            ds[2 * t] = pp.x * (__uint_as_float(rd[c4 * 8 + 2 * t]) - D);
+            ds[2 * t + 1] = pp.y * (__uint_as_float(rd[c4 * 8 + 2 * t + 1]) - D);
+          }
+          const int chunk = c * 4 + c4;
+          st_chunk(sdS + (chunk >> 3) * TILE_BYTES, row, chunk & 7, ds, 0.125f);
+        }
+      }
+      fence_proxy_async_smem();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_p);
+      mbar_wait(b_o, ph);
+      tcgen05_fence_after();
+      // epilogue: dQ -> sQ, dK -> sK, dV -> sV (all input tiles are dead once b_o has fired), then 3 TMA stores
+#pragma unroll
+      for (int which = 0; which < 3; ++which) {
+        const uint32_t t0 = which == 0 ? tdQ : (which == 1 ? tdK : tdV);
+        uint8_t* dst = which == 0 ? sQ : (which == 1 ? sK : sV);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(t0 + lane_addr + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            float v[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(r[c4 * 8 + t]);
+            st_chunk(dst, row, c * 4 + c4, v, 1.f);
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      tcgen05_fence_before();
+      named_bar_sync(2, SM_THREADS);
+      if (tid == 0) {
+        tma_store_3d(&tm_dqkv, smem_u32(sQ), h * 64, 0, seq);
+        tma_store_3d(&tm_dqkv, smem_u32(sK), H + h * 64, 0, seq);
+        tma_store_3d(&tm_dqkv, smem_u32(sV), 2 * H + h * 64, 0, seq);
+        tma_store_commit();
+        tma_store_wait_read();
+        mbar_arrive(b_free);
+      }
+      ph ^= 1;
+    }
+    if (tid == 0) tma_store_wait_all();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// bf16 [nseq, S, cols] (row stride `cols` elements), box = [1, 128 rows, 64 cols], 128B swizzle
+int make_tmap3(CUtensorMap* out, const void* base, int nseq, int S, long long cols) {
+  EncodeTiledFn fn = encode_fn();
+  DPRB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  DPRB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && cols % 8 == 0, "attention operand misaligned");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)S, (cuuint64_t)nseq};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)S * cols * 2};
+  cuuint32_t box[3] = {64u, 128u, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DPRB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed with CUresult %d", (int)r);
+  return 0;
+}
+
+}  // namespace
+
+int attn_fwd_tc(const void* qkv, const int32_t* attn_mask, void* ctx, float* lse, int nseq, int S, int heads,
+                cudaStream_t stream) {
+  const int H = heads * 64;
+  CUtensorMap tq, tc;
+  if (int rc = make_tmap3(&tq, qkv, nseq, S, 3LL * H)) return rc;
+  if (int rc = make_tmap3(&tc, ctx, nseq, S, H)) return rc;
+  static bool attr = false;
+  if (!attr) {
+    DPRB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    attr = true;
+  }
+  int sms = num_sms();
+  if (sms <= 0) sms = 148;
+  const int nprob = nseq * heads;
+  const int grid = nprob < 2 * sms ? nprob : 2 * sms;
+  attn_fwd_tc_kernel<<<grid, NTHREADS, FWD_SMEM, stream>>>(tq, tc, attn_mask, lse, S, heads, nseq);
+  DPRB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int attn_bwd_tc(const void* qkv, const int32_t* attn_mask, const float* lse, const void* dctx, void* dqkv, int nseq,
+                int S, int heads, cudaStream_t stream) {
+  const int H = heads * 64;
+  CUtensorMap tq, tdo, tdq;
+  if (int rc = make_tmap3(&tq, qkv, nseq, S, 3LL * H)) return rc;
+  if (int rc = make_tmap3(&tdo, dctx, nseq, S, H)) return rc;
+  if (int rc = make_tmap3(&tdq, dqkv, nseq, S, 3LL * H)) return rc;
+  static bool attr = false;
+  if (!attr) {
+    DPRB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    attr = true;
+  }
+  int sms = num_sms();
+  if (sms <= 0) sms = 148;
+  const int nprob = nseq * heads;
+  const int grid = nprob < sms ? nprob : sms;
+  attn_bwd_tc_kernel<<<grid, NTHREADS, BWD_SMEM, stream>>>(tq, tdo, tdq, attn_mask, lse, S, heads, nseq);
+  DPRB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace dprb

@@ -273,3 +273,8 @@ CHECKS = {
     "score_ce_small": lambda: check_score_ce(Q=8, C=16, d=128, inv_t=1.0, q0=0, nq=8, c0=0, nc=16),
     "adamw": lambda: check_adamw(),
 }
+
+# tcgen05 attention (S <= 128) extra shapes: many problems (persistent loop, barrier phases), heads=12
+CHECKS["attn_tc_many"] = lambda: check_attention(40, 128, 12, True, seed=9)
+CHECKS["attn_tc_s64_many"] = lambda: check_attention(33, 64, 4, True, seed=10)
+CHECKS["attn_tc_s37"] = lambda: check_attention(5, 37, 2, True, seed=11)

@@ -14,6 +14,8 @@ namespace {
 
 constexpr int WARPS = 8;
 constexpr int THREADS = WARPS * 32;
+constexpr int PF_DEPTH = 4;  // rows of dy / z in flight per warp in the LayerNorm backward
+
 
 __device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
   uint4 q = *reinterpret_cast<const uint4*>(p);
@@ -171,35 +173,49 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ dy_cls, int
 #pragma unroll
     for (int j = 0; j < 8; ++j) { ag[i][j] = 0.f; ab[i][j] = 0.f; az[i][j] = 0.f; az1[i][j] = 0.f; }
   }
-  // Software prefetch: the packed (bf16) dy / z chunks of the NEXT row are requested before the current row is
-  // reduced, doubling the bytes in flight per warp (the kernel is latency-bound at 1 CTA/SM otherwise).
+  // Dense path: each lane stages its own 16-byte chunks of the next PF_DEPTH rows in shared memory with cp.async
+  // (a per-lane FIFO: no cross-lane visibility needed), so PF_DEPTH rows of dy and z are in flight per warp —
+  // at one 8-warp CTA per SM (register-bound) a single row in flight leaves the kernel latency-bound at ~2.5 TB/s.
   const bool sparse_dy = (dy_cls != nullptr);
   const bool dense_path = !EMBED && !sparse_dy;
-  uint4 nz[MAXC], ndy[MAXC];
-  if (dense_path && warp_global < T) {
+  constexpr int SLOT_BYTES = 2 * MAXC * 512 + 16;  // z chunks | dy chunks | (mean, rstd)
+  uint8_t* ring = reinterpret_cast<uint8_t*>(smem_f) + (size_t)(threadIdx.x >> 5) * PF_DEPTH * SLOT_BYTES;
+  auto stage = [&](int r, int slot) {
+    if (r < T) {
 #pragma unroll
-    for (int i = 0; i < MAXC; ++i)
-      if (act[i]) {
-        const long long o = (long long)warp_global * H + (lane + 32 * i) * 8;
-        nz[i] = ldg_nc_v4(z + o);
-        ndy[i] = ldg_nc_v4(dy + o);
-      }
+      for (int i = 0; i < MAXC; ++i)
+        if (act[i]) {
+          const long long o = (long long)r * H + (lane + 32 * i) * 8;
+          uint8_t* dst = ring + slot * SLOT_BYTES + i * 512 + lane * 16;
+          cp_async_16(dst, z + o);
+          cp_async_16(dst + MAXC * 512, dy + o);
+        }
+      if (lane == 0) cp_async_8(ring + slot * SLOT_BYTES + 2 * MAXC * 512, stats + 2 * (long long)r);
+    }
+    cp_async_commit();
+  };
+  if (dense_path) {
+#pragma unroll
+    for (int d = 0; d < PF_DEPTH - 1; ++d) stage(warp_global + d * nwarps, d);
   }
-  for (int row = warp_global; row < T; row += nwarps) {
+  int it = 0;
+  for (int row = warp_global; row < T; row += nwarps, ++it) {
     uint4 cz[MAXC], cdy[MAXC];
+    float pf_mean = 0.f, pf_rstd = 0.f;
     if (dense_path) {
+      stage(row + (PF_DEPTH - 1) * nwarps, (it + PF_DEPTH - 1) % PF_DEPTH);
+      cp_async_wait<PF_DEPTH - 1>();
+      const int slot = it % PF_DEPTH;
 #pragma unroll
-      for (int i = 0; i < MAXC; ++i) { cz[i] = nz[i]; cdy[i] = ndy[i]; }
-      const int nrow = row + nwarps;
-      if (nrow < T) {
-#pragma unroll
-        for (int i = 0; i < MAXC; ++i)
-          if (act[i]) {
-            const long long o = (long long)nrow * H + (lane + 32 * i) * 8;
-            nz[i] = ldg_nc_v4(z + o);
-            ndy[i] = ldg_nc_v4(dy + o);
-          }
-      }
+      for (int i = 0; i < MAXC; ++i)
+        if (act[i]) {
+          const uint8_t* src = ring + slot * SLOT_BYTES + i * 512 + lane * 16;
+          cz[i] = *reinterpret_cast<const uint4*>(src);
+          cdy[i] = *reinterpret_cast<const uint4*>(src + MAXC * 512);
+        }
+      __syncwarp();  // lane 0's (mean, rstd) copy must be visible to the whole warp
+      const float2 st = *reinterpret_cast<const float2*>(ring + slot * SLOT_BYTES + 2 * MAXC * 512);
+      pf_mean = st.x; pf_rstd = st.y;
     }
     if (sparse_dy && (row % cls_stride != 0)) {
       // upstream gradient is identically zero for this row
@@ -210,7 +226,8 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ dy_cls, int
       }
       continue;
     }
-    const float mean = stats[2 * (long long)row], rstd = stats[2 * (long long)row + 1];
+    const float mean = dense_path ? pf_mean : stats[2 * (long long)row];
+    const float rstd = dense_path ? pf_rstd : stats[2 * (long long)row + 1];
     long long id = 0, tt = 0, pp = 0;
     if (EMBED) { id = ids[row]; tt = tts ? tts[row] : 0; pp = pids[row]; }
     float xh[MAXC][8], d[MAXC][8];
@@ -274,6 +291,7 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ dy_cls, int
       }
     }
   }
+  cp_async_wait<0>();
   flush_cols<MAXC>(ag, act, smem_f, dgamma, H);
   flush_cols<MAXC>(ab, act, smem_f, dbeta, H);
   if (EMBED) {
@@ -370,7 +388,18 @@ int ln_bwd(const void* dy, const float* dy_cls, int cls_stride, const void* z, c
   DPRB_REQUIRE((dy != nullptr) != (dy_cls != nullptr), "ln_bwd: exactly one of dy / dy_cls must be given");
   DPRB_REQUIRE(dy_cls == nullptr || cls_stride > 0, "ln_bwd: cls_stride must be positive");
   const int grid = grid_for_rows(T);
-  const size_t smem = (size_t)WARPS * H * sizeof(float);
+  const int maxc = (H + 255) / 256;
+  size_t smem = (size_t)WARPS * H * sizeof(float);
+  const size_t ring = (size_t)WARPS * PF_DEPTH * (2 * maxc * 512 + 16);
+  if (ring > smem) smem = ring;
+  static bool attr = false;
+  if (!attr) {
+    DPRB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    DPRB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    DPRB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    DPRB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr = true;
+  }
 #define CALL(C) ln_bwd_kernel<C, false><<<grid, THREADS, smem, stream>>>((const bf16*)dy, dy_cls, cls_stride > 0 ? cls_stride : 1, (const bf16*)z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stats, gamma, (bf16*)dz, nullptr, nullptr, nullptr, dgamma, dbeta, dbias, T, H)
   DISPATCH_MAXC(H, CALL);
 #undef CALL

@@ -64,6 +64,7 @@ struct GemmParams {
   bf16* out2;          // EPI_BIAS_GELU: pre-activation store, ld = ldd
   float alpha;         // scale applied to the accumulator before the epilogue
   float* colsum;       // optional: colsum[n] += sum_m D(m, n) of the bf16-rounded output (bias gradients)
+  int aux_prefetch;    // 1: request aux with cp.async before waiting for the accumulator (CG = 2 only)
 };
 
 // ---- cluster / 2-CTA helpers -------------------------------------------------------------------------------
@@ -274,10 +275,44 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int u = worker; u < units; u += num_workers) {
       const int tile = u % tiles;
       const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tcgen05_fence_after();
       const int row0 = m_blk * m_rows_per_unit + (int)cta_rank * CTA_M + quarter * 32;
       const int row = row0 + lane;
+      // aux (residual / pre-activation) does not depend on the accumulator: request both of this warp's slabs with
+      // cp.async BEFORE waiting for the MMA, and pull the next tile's aux lines into L2, so the DRAM latency of the
+      // epilogue operand hides behind the tensor-core work instead of sitting on the epilogue's critical path.
+      const bool aux_pf = has_aux && NSLAB == 2 && p.aux_prefetch;
+      if (aux_pf) {
+        if (lane == 0) tma_store_wait_read_n(0);
+        __syncwarp();
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          const int colbase = n_blk * BLOCK_N + col_half * 128 + sl * 64;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int idx = lane + 32 * i, r = idx >> 3, ch = idx & 7;
+            const bool ok = row0 + r < p.M && colbase + ch * 8 < p.N;
+            const bf16* src = ok ? p.aux + (long long)(row0 + r) * p.ld_aux + colbase + ch * 8 : p.aux;
+            cp_async_16_zfill(slab_base + sl * SLAB_BYTES + r * 128 + ((ch ^ (r & 7)) << 4), src, ok);
+          }
+        }
+        cp_async_commit();
+        const int un = u + num_workers;
+        if (un < units) {
+          const int tn = un % tiles;
+          const int rn = (tn / p.num_n_blocks) * m_rows_per_unit + (int)cta_rank * CTA_M + quarter * 32 + lane;
+          const int cn = (tn % p.num_n_blocks) * BLOCK_N + col_half * 128;
+          if (rn < p.M && cn < p.N) {
+            prefetch_l2(p.aux + (long long)rn * p.ld_aux + cn);
+            if (cn + 64 < p.N) prefetch_l2(p.aux + (long long)rn * p.ld_aux + cn + 64);
+          }
+        }
+      }
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      if (aux_pf) {
+        cp_async_wait<0>();
+        __syncwarp();
+      }
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + col_half * 128);
       if (f32_out) {
         const bool row_ok = row < p.M;
@@ -367,11 +402,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int sl = 0; sl < 2; ++sl) {          // two 64-column slabs per warp
           const int colbase = n_blk * BLOCK_N + col_half * 128 + sl * 64;
           if (colbase >= p.N) break;              // warp-uniform
-          uint8_t* slab = slab_base + slab_sel * SLAB_BYTES;
-          // the TMA store that last used this slab must have finished READING it before it is overwritten
-          if (lane == 0) tma_store_wait_read_n(NSLAB - 1);
-          __syncwarp();
-          if (has_aux) {
+          uint8_t* slab = slab_base + (aux_pf ? sl : slab_sel) * SLAB_BYTES;
+          if (!aux_pf) {
+            // the TMA store that last used this slab must have finished READING it before it is overwritten
+            if (lane == 0) tma_store_wait_read_n(NSLAB - 1);
+            __syncwarp();
+          }
+          if (has_aux && !aux_pf) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int idx = lane + 32 * i, r = idx >> 3, ch = idx & 7;
@@ -587,6 +624,10 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long l
   p.D = D; p.ldd = ldd; p.bias = bias; p.aux = reinterpret_cast<const bf16*>(aux); p.ld_aux = ld_aux;
   p.out2 = reinterpret_cast<bf16*>(out2); p.alpha = alpha;
   p.colsum = colsum;
+  static const bool no_aux_pf = (std::getenv("DPRB_NO_AUX_PF") != nullptr);
+  // measured (same box, cfg-2 shapes): prefetching aux before the accumulator wait gains 10-14 % where the epilogue
+  // is the critical path (K <= 1024: attention-out, dGELU) and costs ~1.5 % on the K >= 2304 GEMMs
+  p.aux_prefetch = (no_aux_pf || K > 1024) ? 0 : 1;
   DPRB_REQUIRE(colsum == nullptr || (!f32_out && epilogue != DPRB_EPI_BIAS_GELU),
                "gemm: colsum is supported for the BIAS / BIAS_RESIDUAL / DGELU epilogues only");
 

@@ -58,7 +58,7 @@ SIGNATURES = {
     "dprb_ln_bwd": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
     "dprb_colsum_bf16": (c_int, [_P, c_int64, _P, c_int, c_int, _P]),
     "dprb_attn_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
-    "dprb_attn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "dprb_attn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "dprb_score_ce_fwd": (c_int, [_P, _P, _P, _P, _P, c_float, _P, _P, _P, c_int, c_int, c_int, _P]),
     "dprb_score_ce_bwd": (c_int, [_P, _P, _P, _P, _P, c_float, c_float, _P, _P, c_int, c_int, c_int, c_int,
                                   c_int, c_int, c_int, _P]),

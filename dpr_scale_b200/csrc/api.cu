@@ -84,8 +84,8 @@ int dprb_attn_fwd(const void* qkv, const int32_t* attn_mask, void* ctx, float* l
   return attn_fwd_lse(qkv, attn_mask, ctx, lse, nseq, Sq, heads, S(stream));
 }
 int dprb_attn_bwd(const void* qkv, const int32_t* attn_mask, const void* ctx, const float* lse, const void* dctx,
-                  void* dqkv, int nseq, int Sq, int heads, dprb_stream_t stream) {
-  return attn_bwd_lse(qkv, attn_mask, ctx, lse, dctx, dqkv, nseq, Sq, heads, S(stream));
+                  void* dqkv, float* dbias, int nseq, int Sq, int heads, dprb_stream_t stream) {
+  return attn_bwd_lse(qkv, attn_mask, ctx, lse, dctx, dqkv, dbias, nseq, Sq, heads, S(stream));
 }
 int dprb_score_ce_fwd(const float* q, const float* c, const uint8_t* col_mask, const uint8_t* pair_mask,
                       const int64_t* labels, float inv_temperature, float* lse, float* loss_sum, float* logits,

@@ -393,11 +393,11 @@ int attn_fwd_lse(const void* qkv, const int32_t* attn_mask, void* ctx, float* ls
 }
 
 int attn_bwd_lse(const void* qkv, const int32_t* attn_mask, const void* ctx, const float* lse, const void* dctx,
-                 void* dqkv, int nseq, int S, int heads, cudaStream_t stream) {
+                 void* dqkv, float* dbias, int nseq, int S, int heads, cudaStream_t stream) {
   if (int rc = check_shape(nseq, S, heads, "attn_bwd")) return rc;
   if (nseq == 0) return 0;
   static const bool legacy = (std::getenv("DPRB_ATTN_LEGACY") != nullptr);
-  if (S <= 128 && !legacy) return attn_bwd_tc(qkv, attn_mask, lse, dctx, dqkv, nseq, S, heads, stream);  // tcgen05 path
+  if (S <= 128 && !legacy) return attn_bwd_tc(qkv, attn_mask, lse, dctx, dqkv, dbias, nseq, S, heads, stream);  // tcgen05 path
   const int S_pad = (S + 63) / 64 * 64;
   const size_t smem = 4 * (size_t)S_pad * 128 + 3 * S_pad * 4 + 8 * 16 * STG_STRIDE;
   static bool attr = false;
@@ -409,6 +409,8 @@ int attn_bwd_lse(const void* qkv, const int32_t* attn_mask, const void* ctx, con
   attn_bwd_kernel<<<grid, 256, smem, stream>>>((const bf16*)qkv, attn_mask, (const bf16*)ctx, lse, (const bf16*)dctx,
                                               (bf16*)dqkv, S, S_pad, heads);
   DPRB_CHECK_CUDA(cudaGetLastError());
+  // legacy (mma.sync) path: the QKV bias gradient is a separate streaming pass
+  if (dbias != nullptr) return colsum_bf16(dqkv, 3LL * heads * DH, dbias, nseq * S, 3 * heads * DH, stream);
   return 0;
 }
 

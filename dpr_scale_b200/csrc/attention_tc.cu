@@ -200,26 +200,29 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------ backward
-// smem: sQ | sK | sV | sdO | sP (2 blocks) | sdS (2 blocks) | mask[2][128] | barriers  (~129 KB, 1 CTA/SM)
+// 1 control warp + 8 compute warps.  Two warps share each TMEM lane quarter and split the 128 key columns in halves.
+// Inputs (Q, K, V, dO) are double-buffered: the tiles of problem n+1 are requested while problem n is processed.
+// smem: 2 x (sQ | sK | sV | sdO) | sP (2 blocks) | sdS (2 blocks) | mask[2][128] | Dpart[2][128] | barriers (~195 KB)
 // TMEM: S [0,128) dP [128,256) dV [256,320) dK [320,384) dQ [384,448)
-constexpr int BWD_SMEM = 4 * TILE_BYTES + 4 * TILE_BYTES + 2 * 128 * 4 + 64 + 1024;
+constexpr int BWD_CW = 8;                       // compute warps
+constexpr int BWD_CT = BWD_CW * 32;             // compute threads
+constexpr int BWD_THREADS = 32 + BWD_CT;
+constexpr int BWD_SMEM = 8 * TILE_BYTES + 4 * TILE_BYTES + 4 * 128 * 4 + 128 + 1024;
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_dctx,
                    const __grid_constant__ CUtensorMap tm_dqkv, const int32_t* __restrict__ attn_mask,
-                   const float* __restrict__ lse_in, int S, int heads, int nseq) {
+                   const float* __restrict__ lse_in, float* __restrict__ dbias, int S, int heads, int nseq) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + TILE_BYTES;
-  uint8_t* sV = sK + TILE_BYTES;
-  uint8_t* sdO = sV + TILE_BYTES;
-  uint8_t* sP = sdO + TILE_BYTES;      // 2 x 16 KB  [i][j]
-  uint8_t* sdS = sP + 2 * TILE_BYTES;  // 2 x 16 KB  [i][j]
-  float* sMask = reinterpret_cast<float*>(sdS + 2 * TILE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + 256);
-  uint64_t *b_load = bars, *b_s = bars + 1, *b_p = bars + 2, *b_o = bars + 3, *b_free = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint8_t* sIn = smem;                       // [2][4][TILE_BYTES]: Q, K, V, dO
+  uint8_t* sP = sIn + 8 * TILE_BYTES;        // 2 x 16 KB  [i][j]
+  uint8_t* sdS = sP + 2 * TILE_BYTES;        // 2 x 16 KB  [i][j]
+  float* sMask = reinterpret_cast<float*>(sdS + 2 * TILE_BYTES);  // [2][128]
+  float* sDp = sMask + 256;                                       // [2][128] partial D per column half
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDp + 256);
+  uint64_t *b_load = bars /*[2]*/, *b_s = bars + 2, *b_p = bars + 3, *b_o = bars + 4, *b_free = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = heads * 64;
@@ -228,7 +231,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       tma_prefetch_desc(&tm_qkv);
       tma_prefetch_desc(&tm_dctx);
       tma_prefetch_desc(&tm_dqkv);
-      mbar_init(b_load, 1); mbar_init(b_s, 1); mbar_init(b_p, 4); mbar_init(b_o, 1); mbar_init(b_free, 1);
+      mbar_init(&b_load[0], 1); mbar_init(&b_load[1], 1);
+      mbar_init(b_s, 1); mbar_init(b_p, BWD_CW); mbar_init(b_o, 1); mbar_init(b_free, 4);
       fence_barrier_init();
     }
     __syncwarp();
@@ -246,17 +250,26 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       constexpr uint32_t idesc_s = make_idesc_bf16_f32(128, 128, 0, 0);    // Q K^T, dO V^T
       constexpr uint32_t idesc_t = make_idesc_bf16_f32(128, 64, 1, 1);     // P^T dO, dS^T Q
       constexpr uint32_t idesc_q = make_idesc_bf16_f32(128, 64, 0, 1);     // dS K
-      uint32_t ph = 0;
-      for (int prob = blockIdx.x; prob < nprob; prob += gridDim.x) {
+      auto issue_loads = [&](int prob, int buf) {
         const int seq = prob / heads, h = prob - seq * heads;
-        mbar_wait(b_free, ph ^ 1);
-        mbar_arrive_expect_tx(b_load, 4 * TILE_BYTES);
-        tma_load_3d(sQ, &tm_qkv, b_load, h * 64, 0, seq);
-        tma_load_3d(sK, &tm_qkv, b_load, H + h * 64, 0, seq);
-        tma_load_3d(sV, &tm_qkv, b_load, 2 * H + h * 64, 0, seq);
-        tma_load_3d(sdO, &tm_dctx, b_load, h * 64, 0, seq);
-        mbar_wait(b_load, ph);
+        uint8_t* base = sIn + buf * 4 * TILE_BYTES;
+        mbar_arrive_expect_tx(&b_load[buf], 4 * TILE_BYTES);
+        tma_load_3d(base, &tm_qkv, &b_load[buf], h * 64, 0, seq);
+        tma_load_3d(base + TILE_BYTES, &tm_qkv, &b_load[buf], H + h * 64, 0, seq);
+        tma_load_3d(base + 2 * TILE_BYTES, &tm_qkv, &b_load[buf], 2 * H + h * 64, 0, seq);
+        tma_load_3d(base + 3 * TILE_BYTES, &tm_dctx, &b_load[buf], h * 64, 0, seq);
+      };
+      if ((int)blockIdx.x < nprob) issue_loads(blockIdx.x, 0);
+      int it = 0;
+      for (int prob = blockIdx.x; prob < nprob; prob += gridDim.x, ++it) {
+        const int buf = it & 1;
+        // the previous problem's epilogue (staged in the other buffer) must have drained before that buffer is reloaded
+        if (it > 0) mbar_wait(b_free, (it - 1) & 1);
+        if (prob + (int)gridDim.x < nprob) issue_loads(prob + gridDim.x, buf ^ 1);
+        mbar_wait(&b_load[buf], (it >> 1) & 1);
         tcgen05_fence_after();
+        uint8_t* sQ = sIn + buf * 4 * TILE_BYTES;
+        uint8_t *sK = sQ + TILE_BYTES, *sV = sQ + 2 * TILE_BYTES, *sdO = sQ + 3 * TILE_BYTES;
         const uint64_t dq = desc_kmajor(smem_u32(sQ)), dk = desc_kmajor(smem_u32(sK));
         const uint64_t dv = desc_kmajor(smem_u32(sV)), ddo = desc_kmajor(smem_u32(sdO));
 #pragma unroll
@@ -264,7 +277,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_f16(tdP, ddo + 2 * k, dv + 2 * k, idesc_s, k > 0);
         umma_commit(b_s);
-        mbar_wait(b_p, ph);
+        mbar_wait(b_p, it & 1);
         tcgen05_fence_after();
         // transposed A operands: the [i][j] tiles read MN-major (M = j: two 64-wide atoms 16 KB apart; K = i)
         const uint64_t dpt = desc_mnmajor(smem_u32(sP), TILE_BYTES), dst = desc_mnmajor(smem_u32(sdS), TILE_BYTES);
@@ -279,36 +292,39 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           umma_f16(tdQ, a, bk + 128 * k, idesc_q, k > 0);
         }
         umma_commit(b_o);
-        ph ^= 1;
       }
     }
     __syncwarp();
   } else {
-    const int tid = threadIdx.x - 32;
-    const int quarter = warp & 3;
+    const int tid = threadIdx.x - 32;            // 0..255
+    const int cw = warp - 1;                     // 0..7
+    const int quarter = warp & 3;                // TMEM lane quarter
+    const int half = cw >> 2;                    // which 64 of the 128 key columns / which 32 of the 64 output columns
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    uint32_t ph = 0;
-    for (int prob = blockIdx.x; prob < nprob; prob += gridDim.x) {
+    int it = 0;
+    for (int prob = blockIdx.x; prob < nprob; prob += gridDim.x, ++it) {
       const int seq = prob / heads, h = prob - seq * heads;
-      float* mk = sMask + ph * 128;
-      {
+      const int buf = it & 1;
+      float* mk = sMask + buf * 128;
+      float* dpart = sDp + buf * 128 * 0;  // single buffer: guarded by the named barriers below
+      if (tid < 128) {
         const bool keep = tid < S && (attn_mask == nullptr || attn_mask[(long long)seq * S + tid] != 0);
         mk[tid] = keep ? 0.f : -INFINITY;
       }
       // rows beyond S: lse = +inf  =>  P = 0
       const float lse2 = row < S ? lse_in[((long long)seq * heads + h) * S + row] * LOG2E : INFINITY;
-      named_bar_sync(1, SM_THREADS);
-      mbar_wait(b_s, ph);
+      named_bar_sync(1, BWD_CT);
+      mbar_wait(b_s, it & 1);
       tcgen05_fence_after();
-      // pass 1: P (kept packed in registers + written to smem) and D_i = sum_j P_ij dP_ij
-      uint32_t pk[64];
+      // pass 1 (own 64 columns): P (packed in registers + smem block `half`), partial D_i = sum_j P_ij dP_ij
+      uint32_t pk[32];
       float D = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t rs[32], rd[32];
-        tmem_ld_32x32(tS + lane_addr + c * 32, rs);
-        tmem_ld_32x32(tdP + lane_addr + c * 32, rd);
+        tmem_ld_32x32(tS + lane_addr + half * 64 + c * 32, rs);
+        tmem_ld_32x32(tdP + lane_addr + half * 64 + c * 32, rd);
         tmem_ld_wait();
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
@@ -316,21 +332,24 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
             const int j = c4 * 8 + t;
-            p[t] = ex2_approx(fmaf(__uint_as_float(rs[j]), SCALE_LOG2, mk[c * 32 + j]) - lse2);
+            p[t] = ex2_approx(fmaf(__uint_as_float(rs[j]), SCALE_LOG2, mk[half * 64 + c * 32 + j]) - lse2);
             D = fmaf(p[t], __uint_as_float(rd[j]), D);
           }
 #pragma unroll
           for (int t = 0; t < 4; ++t) pk[c * 16 + c4 * 4 + t] = pack_bf16x2(p[2 * t], p[2 * t + 1]);
-          const int chunk = c * 4 + c4;
+          const int chunk = c * 4 + c4;  // 16-byte chunk inside this half's 64-column block
           uint4 q = make_uint4(pk[c * 16 + c4 * 4], pk[c * 16 + c4 * 4 + 1], pk[c * 16 + c4 * 4 + 2], pk[c * 16 + c4 * 4 + 3]);
-          *reinterpret_cast<uint4*>(sP + (chunk >> 3) * TILE_BYTES + row * 128 + (((chunk & 7) ^ (row & 7)) << 4)) = q;
+          *reinterpret_cast<uint4*>(sP + half * TILE_BYTES + row * 128 + ((chunk ^ (row & 7)) << 4)) = q;
         }
       }
+      dpart[half * 128 + row] = D;
+      named_bar_sync(2, BWD_CT);
+      D = dpart[row] + dpart[128 + row];
       // pass 2: dS = P (dP - D) / sqrt(dh)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t rd[32];
-        tmem_ld_32x32(tdP + lane_addr + c * 32, rd);
+        tmem_ld_32x32(tdP + lane_addr + half * 64 + c * 32, rd);
         tmem_ld_wait();
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
@@ -341,49 +360,65 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             ds[2 * t] = pp.x * (__uint_as_float(rd[c4 * 8 + 2 * t]) - D);
             ds[2 * t + 1] = pp.y * (__uint_as_float(rd[c4 * 8 + 2 * t + 1]) - D);
           }
-          const int chunk = c * 4 + c4;
-          st_chunk(sdS + (chunk >> 3) * TILE_BYTES, row, chunk & 7, ds, 0.125f);
+          st_chunk(sdS + half * TILE_BYTES, row, c * 4 + c4, ds, 0.125f);
         }
       }
       fence_proxy_async_smem();
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(b_p);
-      mbar_wait(b_o, ph);
+      mbar_wait(b_o, it & 1);
       tcgen05_fence_after();
-      // epilogue: dQ -> sQ, dK -> sK, dV -> sV (all input tiles are dead once b_o has fired), then 3 TMA stores
+      // epilogue: dQ -> sQ, dK -> sK, dV -> sV of this problem's input buffer (dead once b_o has fired);
+      // this warp converts columns [32*half, +32) of its 32 rows for each of the three tiles
+      uint8_t* sQ = sIn + buf * 4 * TILE_BYTES;
 #pragma unroll
       for (int which = 0; which < 3; ++which) {
         const uint32_t t0 = which == 0 ? tdQ : (which == 1 ? tdK : tdV);
-        uint8_t* dst = which == 0 ? sQ : (which == 1 ? sK : sV);
+        uint8_t* dst = sQ + which * TILE_BYTES;
+        uint32_t r[32];
+        tmem_ld_32x32(t0 + lane_addr + half * 32, r);
+        tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(t0 + lane_addr + c * 32, r);
-          tmem_ld_wait();
+        for (int c4 = 0; c4 < 4; ++c4) {
+          float v[8];
 #pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            float v[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(r[c4 * 8 + t]);
-            st_chunk(dst, row, c * 4 + c4, v, 1.f);
-          }
+          for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(r[c4 * 8 + t]);
+          st_chunk(dst, row, half * 4 + c4, v, 1.f);
         }
       }
       fence_proxy_async_smem();
       tcgen05_fence_before();
-      named_bar_sync(2, SM_THREADS);
-      if (tid == 0) {
-        tma_store_3d(&tm_dqkv, smem_u32(sQ), h * 64, 0, seq);
-        tma_store_3d(&tm_dqkv, smem_u32(sK), H + h * 64, 0, seq);
-        tma_store_3d(&tm_dqkv, smem_u32(sV), 2 * H + h * 64, 0, seq);
-        tma_store_commit();
-        tma_store_wait_read();
-        mbar_arrive(b_free);
+      named_bar_sync(3, BWD_CT);
+      if (cw < 3) {
+        // bias gradient of the fused QKV projection: column sums of the staged (bf16) dQ / dK / dV tiles.
+        // warp cw sums tile cw; lane l owns columns 2l, 2l+1 (a 128-byte row per read: conflict-free)
+        if (dbias != nullptr) {
+          const uint8_t* tile = sQ + cw * TILE_BYTES;
+          float s0 = 0.f, s1 = 0.f;
+          const int nrows = S < 128 ? S : 128;
+          for (int r = 0; r < nrows; ++r) {
+            const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(
+                tile + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4));
+            s0 += f.x; s1 += f.y;
+          }
+          atomicAdd(dbias + cw * H + h * 64 + 2 * lane, s0);
+          atomicAdd(dbias + cw * H + h * 64 + 2 * lane + 1, s1);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_free);
+      } else if (cw == 3) {
+        if (lane == 0) {
+          tma_store_3d(&tm_dqkv, smem_u32(sQ), h * 64, 0, seq);
+          tma_store_3d(&tm_dqkv, smem_u32(sQ + TILE_BYTES), H + h * 64, 0, seq);
+          tma_store_3d(&tm_dqkv, smem_u32(sQ + 2 * TILE_BYTES), 2 * H + h * 64, 0, seq);
+          tma_store_commit();
+          tma_store_wait_read();
+          mbar_arrive(b_free);
+        }
       }
-      ph ^= 1;
     }
-    if (tid == 0) tma_store_wait_all();
+    if (cw == 3 && lane == 0) tma_store_wait_all();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -442,14 +477,14 @@ int attn_fwd_tc(const void* qkv, const int32_t* attn_mask, void* ctx, float* lse
   int sms = num_sms();
   if (sms <= 0) sms = 148;
   const int nprob = nseq * heads;
-  const int grid = nprob < 2 * sms ? nprob : 2 * sms;
+  const int grid = nprob < 2 * sms ? nprob : 2 * sms;  // two co-resident CTAs per SM interleave their serial chains
   attn_fwd_tc_kernel<<<grid, NTHREADS, FWD_SMEM, stream>>>(tq, tc, attn_mask, lse, S, heads, nseq);
   DPRB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-int attn_bwd_tc(const void* qkv, const int32_t* attn_mask, const float* lse, const void* dctx, void* dqkv, int nseq,
-                int S, int heads, cudaStream_t stream) {
+int attn_bwd_tc(const void* qkv, const int32_t* attn_mask, const float* lse, const void* dctx, void* dqkv,
+                float* dbias, int nseq, int S, int heads, cudaStream_t stream) {
   const int H = heads * 64;
   CUtensorMap tq, tdo, tdq;
   if (int rc = make_tmap3(&tq, qkv, nseq, S, 3LL * H)) return rc;
@@ -464,7 +499,7 @@ int attn_bwd_tc(const void* qkv, const int32_t* attn_mask, const float* lse, con
   if (sms <= 0) sms = 148;
   const int nprob = nseq * heads;
   const int grid = nprob < sms ? nprob : sms;
-  attn_bwd_tc_kernel<<<grid, NTHREADS, BWD_SMEM, stream>>>(tq, tdo, tdq, attn_mask, lse, S, heads, nseq);
+  attn_bwd_tc_kernel<<<grid, BWD_THREADS, BWD_SMEM, stream>>>(tq, tdo, tdq, attn_mask, lse, dbias, S, heads, nseq);
   DPRB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

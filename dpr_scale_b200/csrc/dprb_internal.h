@@ -29,12 +29,12 @@ int colsum_bf16(const void* x, long long ld, float* out, int T, int N, cudaStrea
 int attn_fwd_lse(const void* qkv, const int32_t* attn_mask, void* ctx, float* lse, int nseq, int S, int heads,
                  cudaStream_t stream);
 int attn_bwd_lse(const void* qkv, const int32_t* attn_mask, const void* ctx, const float* lse, const void* dctx,
-                 void* dqkv, int nseq, int S, int heads, cudaStream_t stream);
+                 void* dqkv, float* dbias, int nseq, int S, int heads, cudaStream_t stream);
 
 int attn_fwd_tc(const void* qkv, const int32_t* attn_mask, void* ctx, float* lse, int nseq, int S, int heads,
                 cudaStream_t stream);
-int attn_bwd_tc(const void* qkv, const int32_t* attn_mask, const float* lse, const void* dctx, void* dqkv, int nseq,
-                int S, int heads, cudaStream_t stream);
+int attn_bwd_tc(const void* qkv, const int32_t* attn_mask, const float* lse, const void* dctx, void* dqkv,
+                float* dbias, int nseq, int S, int heads, cudaStream_t stream);
 
 int score_ce_fwd(const float* q, const float* c, const uint8_t* col_mask, const uint8_t* pair_mask,
                  const int64_t* labels, float inv_t, float* lse, float* loss_sum, float* logits, int Q, int C, int d,

@@ -390,7 +390,7 @@ class HFEncoder(nn.Module):
         for lo, hi in bounds:
             check(_lib.load().dprb_encoder_bwd(ctypes.byref(w), ctypes.byref(b), dpooled.data_ptr(), lo, hi, stream),
                   "dprb_encoder_bwd")
-            n = 12 * (hi - lo) + (1 if lo == 0 else 0)
+            n = 11 * (hi - lo) + (1 if lo == 0 else 0)
             self.launches += n
             ops._count(n)
             if self.grad_sync is not None:

@@ -110,10 +110,10 @@ def attn_fwd(qkv, attn_mask, nseq, S, heads, need_lse=True):
     return ctx, lse
 
 
-def attn_bwd(qkv, attn_mask, ctx, lse, dctx, nseq, S, heads):
+def attn_bwd(qkv, attn_mask, ctx, lse, dctx, nseq, S, heads, dbias=None):
     dqkv = torch.empty_like(qkv)
-    check(_lib.load().dprb_attn_bwd(_ptr(qkv), _ptr(attn_mask), _ptr(ctx), _ptr(lse), _ptr(dctx), _ptr(dqkv), nseq,
-                                    S, heads, _stream()), "dprb_attn_bwd")
+    check(_lib.load().dprb_attn_bwd(_ptr(qkv), _ptr(attn_mask), _ptr(ctx), _ptr(lse), _ptr(dctx), _ptr(dqkv),
+                                    _ptr(dbias), nseq, S, heads, _stream()), "dprb_attn_bwd")
     _count()
     return dqkv
 

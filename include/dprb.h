@@ -105,8 +105,10 @@ int dprb_colsum_bf16(const void* x_bf16, int64_t ld, float* out, int T, int N, d
  * ------------------------------------------------------------------------------------------- */
 int dprb_attn_fwd(const void* qkv_bf16, const int32_t* attn_mask, void* ctx_bf16, float* lse, int nseq, int S,
                   int heads, dprb_stream_t stream);
+/* dbias (optional, fp32 [3H]): dbias[n] += sum_t dqkv[t, n] — the bias gradient of the fused QKV projection. */
 int dprb_attn_bwd(const void* qkv_bf16, const int32_t* attn_mask, const void* ctx_bf16, const float* lse,
-                  const void* dctx_bf16, void* dqkv_bf16, int nseq, int S, int heads, dprb_stream_t stream);
+                  const void* dctx_bf16, void* dqkv_bf16, float* dbias, int nseq, int S, int heads,
+                  dprb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused in-batch-negative scoring + softmax cross-entropy.

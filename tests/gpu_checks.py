@@ -189,10 +189,12 @@ def check_attention(nseq=3, S=128, heads=2, masked=True, seed=4):
     _close("attn_ctx", ctx, cr, 2 ** -7, 2e-3, res)
     _close("attn_lse", lse, torch.logsumexp(sc, -1), 1e-4, 1e-3, res)
     dctx = _bf(torch.randn(T, H, generator=g))
-    dqkv = ops.attn_bwd(qkv.to(DEV), am.to(DEV) if masked else None, ctx, lse, dctx.to(DEV), nseq, S, heads)
+    dbias = torch.ones(3 * H, device=DEV)
+    dqkv = ops.attn_bwd(qkv.to(DEV), am.to(DEV) if masked else None, ctx, lse, dctx.to(DEV), nseq, S, heads, dbias)
     cr.backward(dctx.float())
     # P and dS are rounded to bf16 before the second matmuls (as in any flash-style kernel): 2^-6 headroom
     _close("attn_dqkv", dqkv, qr.grad, 2 ** -6, 4e-3, res)
+    _close("attn_dbias", dbias, 1 + dqkv.double().cpu().sum(0), 1e-4, 1e-3, res)  # fused QKV bias gradient
     return res
 
 

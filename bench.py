@@ -241,7 +241,8 @@ def run_b200(args, workload):
         dist.init_process_group("nccl", device_id=dev)
     task = DenseRetrieverTask(
         transform={}, datamodule=None, shared_model=False, in_batch_negatives=True, warmup_steps=10,
-        model={"_target_": "dpr_scale_b200.models.hf_model.HFEncoder.from_config", "config": cfg, "dropout": 0.0},
+        model={"_target_": "dpr_scale_b200.models.hf_model.HFEncoder.from_config", "config": cfg,
+               "dropout": args.dropout},
         optim={"_target_": "dpr_scale_b200.optim.FusedAdamW", "lr": 1e-5, "betas": [0.9, 0.999], "eps": 1e-8,
                "weight_decay": 0.0})
     trainer = Trainer(max_steps=10 ** 6, gradient_clip_val=2.0, device=dev)
@@ -311,13 +312,13 @@ def run_b200(args, workload):
         "config": {"workload": workload, "model": "BERT-base x2 (query+context, shared_model=false)",
                    "queries_per_gpu": B, "hard_negatives": n, "contexts_per_gpu": B * (1 + n), "seq_len": S,
                    "global_batch": pairs_step, "parallelism": f"dp{world}", "negatives": "global in-batch" if world > 1 else "in-batch",
-                   "optimizer": "fused AdamW + clip 2.0 + LambdaLR", "dropout": 0.0,
+                   "optimizer": "fused AdamW + clip 2.0 + LambdaLR", "dropout": args.dropout,
                    "l2": "working set (>=40 GB activations + 0.9 GB weights/step) exceeds the 126 MB L2; no flush needed"},
         "e2e": {"value": pairs_step / (ms_e2e / 1e3), "unit": "pairs/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": batch_bytes(host_batch), "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05 UMMA 128x256x16)",
+        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel<*,*,2> (tcgen05 cta_group::2 UMMA 256x256x16)",
                      "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tflops / peak_tf,
                      "peak_source": peak_src, "traffic": None, "gemm_launches": nl.value,
                      "gemm_ms_per_step": tms.value / args.steps, "gemm_share_of_step": (tms.value / args.steps) / ms_step,
@@ -345,7 +346,8 @@ def main():
     ap.add_argument("--workload", default="bert-base_s128_b128_n7", choices=sorted(WORKLOADS))
     ap.add_argument("--ref-pairs", type=int, default=2, help="pairs per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--dropout", type=float, default=0.0, help="stock arm only")
+    ap.add_argument("--dropout", type=float, default=0.1,
+                    help="hidden + attention dropout of both encoders (reference default 0.1, conf/task/model/hf_model.yaml:5)")
     ap.add_argument("--stock-dtype", default="bf16", choices=["bf16", "fp16"])
     args = ap.parse_args()
     if args.impl == "reference":

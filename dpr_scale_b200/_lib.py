@@ -6,7 +6,7 @@ error is raised immediately (``DprbError``).  Build with ``python __graft_entry_
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_void_p, POINTER, Structure
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p, POINTER, Structure
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libdprb.so")
@@ -38,6 +38,8 @@ class EncoderBatch(Structure):
         ("ids", c_void_p), ("type_ids", c_void_p), ("pos_ids", c_void_p), ("attn_mask", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_int64),
         ("save_for_backward", c_int32),
+        ("dropout_p", c_float),
+        ("dropout_seed", c_uint64),
     ]
 
 
@@ -48,17 +50,20 @@ SIGNATURES = {
     "dprb_last_error": (c_char_p, []),
     "dprb_num_sms": (c_int, []),
     "dprb_gemm_bf16": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_int, c_int,
-                               _P, _P, c_int64, _P, c_float, c_int, _P, _P]),
+                               _P, _P, c_int64, _P, c_float, c_int, _P, c_float, c_uint64, _P]),
     "dprb_gemm_profile_enable": (c_int, [c_int, c_int]),
     "dprb_gemm_profile_read": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int64)]),
     "dprb_embed_ln_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
-                                  c_float, _P]),
-    "dprb_embed_ln_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
+                                  c_float, c_float, c_uint64, _P]),
+    "dprb_embed_ln_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_float,
+                                  c_uint64, _P]),
+    "dprb_dropout_site_seed": (c_uint64, [c_uint64, c_int, c_int]),
+    "dprb_dropout_mask": (c_int, [_P, c_int64, c_float, c_uint64, c_int, c_int, _P]),
     "dprb_ln_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P]),
-    "dprb_ln_bwd": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
+    "dprb_ln_bwd": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P, c_float, c_uint64, _P]),
     "dprb_colsum_bf16": (c_int, [_P, c_int64, _P, c_int, c_int, _P]),
-    "dprb_attn_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
-    "dprb_attn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "dprb_attn_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_float, c_uint64, _P]),
+    "dprb_attn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_uint64, _P]),
     "dprb_score_ce_fwd": (c_int, [_P, _P, _P, _P, _P, c_float, _P, _P, _P, c_int, c_int, c_int, _P]),
     "dprb_score_ce_bwd": (c_int, [_P, _P, _P, _P, _P, c_float, c_float, _P, _P, c_int, c_int, c_int, c_int,
                                   c_int, c_int, c_int, _P]),

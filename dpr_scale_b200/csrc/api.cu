@@ -40,9 +40,10 @@ int dprb_num_sms(void) { return num_sms(); }
 
 int dprb_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int64_t lda, int64_t ldb,
                    int64_t ldd, int a_mn_major, int b_mn_major, int epilogue, const float* bias, const void* aux,
-                   int64_t ld_aux, void* out2, float alpha, int splits, float* colsum, dprb_stream_t stream) {
+                   int64_t ld_aux, void* out2, float alpha, int splits, float* colsum, float dropout_p,
+                   uint64_t dropout_site_seed, dprb_stream_t stream) {
   return gemm_bf16(A, B, D, M, N, K, lda, ldb, ldd, a_mn_major, b_mn_major, epilogue, bias, aux, ld_aux, out2,
-                   alpha, splits, colsum, S(stream));
+                   alpha, splits, colsum, dropout_p, dropout_site_seed, S(stream));
 }
 
 int dprb_gemm_profile_enable(int enable, int max_launches) { return gemm_profile_enable(enable, max_launches); }
@@ -56,36 +57,46 @@ int dprb_gemm_profile_read(double* total_ms, double* total_flops, int64_t* launc
 int dprb_embed_ln_fwd(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, const float* word,
                       const float* pos, const float* type, const float* gamma, const float* beta, void* y,
                       float* stats, int T, int H, int vocab, int max_pos, int type_vocab, float eps,
-                      dprb_stream_t stream) {
+                      float dropout_p, uint64_t dropout_seed, dprb_stream_t stream) {
   return embed_ln_fwd(ids, type_ids, pos_ids, word, pos, type, gamma, beta, y, stats, T, H, vocab, max_pos,
-                      type_vocab, eps, S(stream));
+                      type_vocab, eps, dropout_p, dropout_seed, S(stream));
 }
 int dprb_embed_ln_bwd(const void* dy, const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids,
                       const float* word, const float* pos, const float* type, const float* gamma,
                       const float* stats, float* dword, float* dpos, float* dtype, float* dgamma, float* dbeta,
-                      int T, int H, dprb_stream_t stream) {
+                      int T, int H, float dropout_p, uint64_t dropout_seed, dprb_stream_t stream) {
   return embed_ln_bwd(dy, ids, type_ids, pos_ids, word, pos, type, gamma, stats, dword, dpos, dtype, dgamma,
-                      dbeta, T, H, S(stream));
+                      dbeta, T, H, dropout_p, dropout_seed, S(stream));
 }
 int dprb_ln_fwd(const void* z, const float* gamma, const float* beta, void* y, float* stats, float* cls_out,
                 int cls_stride, int T, int H, float eps, dprb_stream_t stream) {
   return ln_fwd(z, gamma, beta, y, stats, cls_out, cls_stride, T, H, eps, S(stream));
 }
 int dprb_ln_bwd(const void* dy, const float* dy_cls, int cls_stride, const void* z, const float* stats,
-                const float* gamma, void* dz, float* dgamma, float* dbeta, float* dbias, int T, int H,
-                dprb_stream_t stream) {
-  return ln_bwd(dy, dy_cls, cls_stride, z, stats, gamma, dz, dgamma, dbeta, dbias, T, H, S(stream));
+                const float* gamma, void* dz, float* dgamma, float* dbeta, float* dbias, int T, int H, void* dzm,
+                float dropout_p, uint64_t dropout_site_seed, dprb_stream_t stream) {
+  return ln_bwd(dy, dy_cls, cls_stride, z, stats, gamma, dz, dgamma, dbeta, dbias, T, H, dzm, dropout_p,
+                dropout_site_seed, S(stream));
+}
+uint64_t dprb_dropout_site_seed(uint64_t dropout_seed, int layer, int site) {
+  return make_drop(0.5f, dropout_seed, layer, site).seed;
+}
+int dprb_dropout_mask(uint8_t* keep, int64_t n, float dropout_p, uint64_t dropout_seed, int layer, int site,
+                      dprb_stream_t stream) {
+  return dropout_mask(keep, n, dropout_p, dropout_seed, layer, site, S(stream));
 }
 int dprb_colsum_bf16(const void* x, int64_t ld, float* out, int T, int N, dprb_stream_t stream) {
   return colsum_bf16(x, ld, out, T, N, S(stream));
 }
 int dprb_attn_fwd(const void* qkv, const int32_t* attn_mask, void* ctx, float* lse, int nseq, int Sq, int heads,
-                  dprb_stream_t stream) {
-  return attn_fwd_lse(qkv, attn_mask, ctx, lse, nseq, Sq, heads, S(stream));
+                  float dropout_p, uint64_t dropout_site_seed, dprb_stream_t stream) {
+  return attn_fwd_lse(qkv, attn_mask, ctx, lse, nseq, Sq, heads, dropout_p, dropout_site_seed, S(stream));
 }
 int dprb_attn_bwd(const void* qkv, const int32_t* attn_mask, const void* ctx, const float* lse, const void* dctx,
-                  void* dqkv, float* dbias, int nseq, int Sq, int heads, dprb_stream_t stream) {
-  return attn_bwd_lse(qkv, attn_mask, ctx, lse, dctx, dqkv, dbias, nseq, Sq, heads, S(stream));
+                  void* dqkv, float* dbias, int nseq, int Sq, int heads, float dropout_p,
+                  uint64_t dropout_site_seed, dprb_stream_t stream) {
+  return attn_bwd_lse(qkv, attn_mask, ctx, lse, dctx, dqkv, dbias, nseq, Sq, heads, dropout_p, dropout_site_seed,
+                      S(stream));
 }
 int dprb_score_ce_fwd(const float* q, const float* c, const uint8_t* col_mask, const uint8_t* pair_mask,
                       const int64_t* labels, float inv_temperature, float* lse, float* loss_sum, float* logits,

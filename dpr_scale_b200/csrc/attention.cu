@@ -374,11 +374,12 @@ int check_shape(int nseq, int S, int heads, const char* who) {
 }  // namespace
 
 int attn_fwd_lse(const void* qkv, const int32_t* attn_mask, void* ctx, float* lse, int nseq, int S, int heads,
-                 cudaStream_t stream) {
+                 float dropout_p, unsigned long long site_seed, cudaStream_t stream) {
   if (int rc = check_shape(nseq, S, heads, "attn_fwd")) return rc;
   if (nseq == 0) return 0;
   static const bool legacy = (std::getenv("DPRB_ATTN_LEGACY") != nullptr);
-  if (S <= 128 && !legacy) return attn_fwd_tc(qkv, attn_mask, ctx, lse, nseq, S, heads, stream);  // tcgen05 path
+  if (S <= 128 && !legacy) return attn_fwd_tc(qkv, attn_mask, ctx, lse, nseq, S, heads, dropout_p, site_seed, stream);
+  DPRB_REQUIRE(dropout_p == 0.f, "attn_fwd: attention dropout is implemented for S <= 128 (tcgen05 path) only");
   const int S_pad = (S + 63) / 64 * 64;
   const size_t smem = 3 * (size_t)S_pad * 128 + S_pad * 4 + 8 * 16 * STG_STRIDE;
   static bool attr = false;
@@ -393,11 +394,14 @@ int attn_fwd_lse(const void* qkv, const int32_t* attn_mask, void* ctx, float* ls
 }
 
 int attn_bwd_lse(const void* qkv, const int32_t* attn_mask, const void* ctx, const float* lse, const void* dctx,
-                 void* dqkv, float* dbias, int nseq, int S, int heads, cudaStream_t stream) {
+                 void* dqkv, float* dbias, int nseq, int S, int heads, float dropout_p,
+                 unsigned long long site_seed, cudaStream_t stream) {
   if (int rc = check_shape(nseq, S, heads, "attn_bwd")) return rc;
   if (nseq == 0) return 0;
   static const bool legacy = (std::getenv("DPRB_ATTN_LEGACY") != nullptr);
-  if (S <= 128 && !legacy) return attn_bwd_tc(qkv, attn_mask, lse, dctx, dqkv, dbias, nseq, S, heads, stream);  // tcgen05 path
+  if (S <= 128 && !legacy)
+    return attn_bwd_tc(qkv, attn_mask, lse, dctx, dqkv, dbias, nseq, S, heads, dropout_p, site_seed, stream);
+  DPRB_REQUIRE(dropout_p == 0.f, "attn_bwd: attention dropout is implemented for S <= 128 (tcgen05 path) only");
   const int S_pad = (S + 63) / 64 * 64;
   const size_t smem = 4 * (size_t)S_pad * 128 + 3 * S_pad * 4 + 8 * 16 * STG_STRIDE;
   static bool attr = false;

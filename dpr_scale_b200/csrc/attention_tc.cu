@@ -48,7 +48,8 @@ constexpr int FWD_SMEM = 3 * TILE_BYTES + 2 * TILE_BYTES + 2 * 128 * 4 + 64 + 10
 
 __global__ void __launch_bounds__(NTHREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_ctx,
-                   const int32_t* __restrict__ attn_mask, float* __restrict__ lse_out, int S, int heads, int nseq) {
+                   const int32_t* __restrict__ attn_mask, float* __restrict__ lse_out, int S, int heads, int nseq,
+                   Drop drop) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -152,6 +153,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             const int j = c4 * 8 + t;
             p[t] = ex2_approx(fmaf(__uint_as_float(r[j]), SCALE_LOG2, mk[c * 32 + j]) - e);
             l += p[t];
+            // attention-probability dropout (modeling_bert.py: dropout on softmax output): the row sum keeps the
+            // un-dropped value, only the P V operand is masked and rescaled
+            if (drop.on()) p[t] *= drop.mul(((uint64_t)prob * S + row) * S + c * 32 + j);
           }
           const int chunk = c * 4 + c4;
           st_chunk(sP + (chunk >> 3) * TILE_BYTES, row, chunk & 7, p, 1.f);
@@ -212,7 +216,7 @@ constexpr int BWD_SMEM = 8 * TILE_BYTES + 4 * TILE_BYTES + 4 * 128 * 4 + 128 + 1
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_dctx,
                    const __grid_constant__ CUtensorMap tm_dqkv, const int32_t* __restrict__ attn_mask,
-                   const float* __restrict__ lse_in, float* __restrict__ dbias, int S, int heads, int nseq) {
+                   const float* __restrict__ lse_in, float* __restrict__ dbias, int S, int heads, int nseq, Drop drop) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sIn = smem;                       // [2][4][TILE_BYTES]: Q, K, V, dO
@@ -318,7 +322,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       mbar_wait(b_s, it & 1);
       tcgen05_fence_after();
       // pass 1 (own 64 columns): P (packed in registers + smem block `half`), partial D_i = sum_j P_ij dP_ij
+      // With attention dropout: P_d = P * mask/(1-p) feeds dV; dP arrives w.r.t. P_d, so dP_m = dP * mask/(1-p),
+      // D_i = sum_j P_ij dP_m_ij and dS = P (dP_m - D).  The keep bits of this thread's 64 columns live in one register.
       uint32_t pk[32];
+      uint64_t keep = ~0ull;
       float D = 0.f;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -328,17 +335,25 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         tmem_ld_wait();
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
-          float p[8];
+          float p[8], pd[8];
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
             const int j = c4 * 8 + t;
             p[t] = ex2_approx(fmaf(__uint_as_float(rs[j]), SCALE_LOG2, mk[half * 64 + c * 32 + j]) - lse2);
-            D = fmaf(p[t], __uint_as_float(rd[j]), D);
+            float dm = 1.f;
+            if (drop.on()) {
+              dm = drop.mul(((uint64_t)prob * S + row) * S + half * 64 + c * 32 + j);
+              if (dm == 0.f) keep &= ~(1ull << (c * 32 + j));
+            }
+            pd[t] = p[t] * dm;
+            D = fmaf(pd[t], __uint_as_float(rd[j]), D);
           }
 #pragma unroll
           for (int t = 0; t < 4; ++t) pk[c * 16 + c4 * 4 + t] = pack_bf16x2(p[2 * t], p[2 * t + 1]);
           const int chunk = c * 4 + c4;  // 16-byte chunk inside this half's 64-column block
-          uint4 q = make_uint4(pk[c * 16 + c4 * 4], pk[c * 16 + c4 * 4 + 1], pk[c * 16 + c4 * 4 + 2], pk[c * 16 + c4 * 4 + 3]);
+          uint4 q;
+          q.x = pack_bf16x2(pd[0], pd[1]); q.y = pack_bf16x2(pd[2], pd[3]);
+          q.z = pack_bf16x2(pd[4], pd[5]); q.w = pack_bf16x2(pd[6], pd[7]);
           *reinterpret_cast<uint4*>(sP + half * TILE_BYTES + row * 128 + ((chunk ^ (row & 7)) << 4)) = q;
         }
       }
@@ -357,8 +372,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const float2 pp = unpack_bf16x2(pk[c * 16 + c4 * 4 + t]);
-            ds[2 * t] = pp.x * (__uint_as_float(rd[c4 * 8 + 2 * t]) - D);
-            ds[2 * t + 1] = pp.y * (__uint_as_float(rd[c4 * 8 + 2 * t + 1]) - D);
+            const int j0 = c * 32 + c4 * 8 + 2 * t;
+            const float m0 = ((keep >> j0) & 1ull) ? drop.scale : 0.f, m1 = ((keep >> (j0 + 1)) & 1ull) ? drop.scale : 0.f;
+            ds[2 * t] = pp.x * (__uint_as_float(rd[c4 * 8 + 2 * t]) * m0 - D);
+            ds[2 * t + 1] = pp.y * (__uint_as_float(rd[c4 * 8 + 2 * t + 1]) * m1 - D);
           }
           st_chunk(sdS + half * TILE_BYTES, row, c * 4 + c4, ds, 0.125f);
         }
@@ -464,7 +481,9 @@ int make_tmap3(CUtensorMap* out, const void* base, int nseq, int S, long long co
 }  // namespace
 
 int attn_fwd_tc(const void* qkv, const int32_t* attn_mask, void* ctx, float* lse, int nseq, int S, int heads,
-                cudaStream_t stream) {
+                float dropout_p, unsigned long long site_seed, cudaStream_t stream) {
+  Drop drop = make_drop(dropout_p, 0, 0, 0);
+  drop.seed = site_seed;
   const int H = heads * 64;
   CUtensorMap tq, tc;
   if (int rc = make_tmap3(&tq, qkv, nseq, S, 3LL * H)) return rc;
@@ -478,13 +497,16 @@ int attn_fwd_tc(const void* qkv, const int32_t* attn_mask, void* ctx, float* lse
   if (sms <= 0) sms = 148;
   const int nprob = nseq * heads;
   const int grid = nprob < 2 * sms ? nprob : 2 * sms;  // two co-resident CTAs per SM interleave their serial chains
-  attn_fwd_tc_kernel<<<grid, NTHREADS, FWD_SMEM, stream>>>(tq, tc, attn_mask, lse, S, heads, nseq);
+  attn_fwd_tc_kernel<<<grid, NTHREADS, FWD_SMEM, stream>>>(tq, tc, attn_mask, lse, S, heads, nseq, drop);
   DPRB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int attn_bwd_tc(const void* qkv, const int32_t* attn_mask, const float* lse, const void* dctx, void* dqkv,
-                float* dbias, int nseq, int S, int heads, cudaStream_t stream) {
+                float* dbias, int nseq, int S, int heads, float dropout_p, unsigned long long site_seed,
+                cudaStream_t stream) {
+  Drop drop = make_drop(dropout_p, 0, 0, 0);
+  drop.seed = site_seed;
   const int H = heads * 64;
   CUtensorMap tq, tdo, tdq;
   if (int rc = make_tmap3(&tq, qkv, nseq, S, 3LL * H)) return rc;
@@ -499,7 +521,7 @@ int attn_bwd_tc(const void* qkv, const int32_t* attn_mask, const float* lse, con
   if (sms <= 0) sms = 148;
   const int nprob = nseq * heads;
   const int grid = nprob < sms ? nprob : sms;
-  attn_bwd_tc_kernel<<<grid, BWD_THREADS, BWD_SMEM, stream>>>(tq, tdo, tdq, attn_mask, lse, dbias, S, heads, nseq);
+  attn_bwd_tc_kernel<<<grid, BWD_THREADS, BWD_SMEM, stream>>>(tq, tdo, tdq, attn_mask, lse, dbias, S, heads, nseq, drop);
   DPRB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -131,6 +131,23 @@ __device__ __forceinline__ uint32_t hash_u32(uint64_t idx, uint64_t seed) {
 __device__ __forceinline__ bool dropout_keep(uint64_t idx, uint64_t seed, uint32_t thresh) {
   return hash_u32(idx, seed) >= thresh;  // thresh = p * 2^32
 }
+// One dropout site: element `idx` is kept iff hash(idx, seed) >= thresh, kept values are scaled by 1/(1-p).
+// thresh == 0 disables the site (p = 0 / eval mode).  Masks are never stored: backward re-derives them.
+struct Drop {
+  uint64_t seed;
+  uint32_t thresh;
+  float scale;
+  __host__ __device__ bool on() const { return thresh != 0u; }
+  __device__ __forceinline__ float mul(uint64_t idx) const { return dropout_keep(idx, seed, thresh) ? scale : 0.f; }
+};
+inline Drop make_drop(float p, uint64_t seed, int layer, int site) {
+  Drop d;
+  d.seed = seed + (uint64_t)(layer * 8 + site + 1) * 0x9E3779B97F4A7C15ull;
+  d.thresh = (p > 0.f) ? (uint32_t)((double)p * 4294967296.0) : 0u;
+  d.scale = (p > 0.f) ? 1.f / (1.f - p) : 1.f;
+  return d;
+}
+enum { DROP_SITE_EMBED = 0, DROP_SITE_ATTN = 1, DROP_SITE_ATTN_OUT = 2, DROP_SITE_FFN_OUT = 3 };
 
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -7,34 +7,40 @@ namespace dprb {
 
 int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long long lda, long long ldb,
               long long ldd, int a_mn_major, int b_mn_major, int epilogue, const float* bias, const void* aux,
-              long long ld_aux, void* out2, float alpha, int splits, float* colsum, cudaStream_t stream);
+              long long ld_aux, void* out2, float alpha, int splits, float* colsum, float dropout_p,
+              unsigned long long drop_site_seed, cudaStream_t stream);
 
 int gemm_profile_enable(int enable, int max_launches);
 int gemm_profile_read(double* total_ms, double* total_flops, long long* launches);
 
 int embed_ln_fwd(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, const float* word,
                  const float* pos, const float* type, const float* gamma, const float* beta, void* y, float* stats,
-                 int T, int H, int vocab, int max_pos, int type_vocab, float eps, cudaStream_t stream);
+                 int T, int H, int vocab, int max_pos, int type_vocab, float eps, float dropout_p,
+                 unsigned long long seed, cudaStream_t stream);
 int embed_ln_bwd(const void* dy, const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids,
                  const float* word, const float* pos, const float* type, const float* gamma, const float* stats,
                  float* dword, float* dpos, float* dtype, float* dgamma, float* dbeta, int T, int H,
-                 cudaStream_t stream);
+                 float dropout_p, unsigned long long seed, cudaStream_t stream);
 int ln_fwd(const void* z, const float* gamma, const float* beta, void* y, float* stats, float* cls_out,
            int cls_stride, int T, int H, float eps, cudaStream_t stream);
 int ln_bwd(const void* dy, const float* dy_cls, int cls_stride, const void* z, const float* stats,
-           const float* gamma, void* dz, float* dgamma, float* dbeta, float* dbias, int T, int H,
-           cudaStream_t stream);
+           const float* gamma, void* dz, float* dgamma, float* dbeta, float* dbias, int T, int H, void* dzm,
+           float dropout_p, unsigned long long site_seed, cudaStream_t stream);
+int dropout_mask(uint8_t* out, long long n, float p, unsigned long long seed, int layer, int site, cudaStream_t stream);
+unsigned long long drop_site_seed(unsigned long long seed, int layer, int site);
 int colsum_bf16(const void* x, long long ld, float* out, int T, int N, cudaStream_t stream);
 
 int attn_fwd_lse(const void* qkv, const int32_t* attn_mask, void* ctx, float* lse, int nseq, int S, int heads,
-                 cudaStream_t stream);
+                 float dropout_p, unsigned long long site_seed, cudaStream_t stream);
 int attn_bwd_lse(const void* qkv, const int32_t* attn_mask, const void* ctx, const float* lse, const void* dctx,
-                 void* dqkv, float* dbias, int nseq, int S, int heads, cudaStream_t stream);
+                 void* dqkv, float* dbias, int nseq, int S, int heads, float dropout_p,
+                 unsigned long long site_seed, cudaStream_t stream);
 
 int attn_fwd_tc(const void* qkv, const int32_t* attn_mask, void* ctx, float* lse, int nseq, int S, int heads,
-                cudaStream_t stream);
+                float dropout_p, unsigned long long site_seed, cudaStream_t stream);
 int attn_bwd_tc(const void* qkv, const int32_t* attn_mask, const float* lse, const void* dctx, void* dqkv,
-                float* dbias, int nseq, int S, int heads, cudaStream_t stream);
+                float* dbias, int nseq, int S, int heads, float dropout_p, unsigned long long site_seed,
+                cudaStream_t stream);
 
 int score_ce_fwd(const float* q, const float* c, const uint8_t* col_mask, const uint8_t* pair_mask,
                  const int64_t* labels, float inv_t, float* lse, float* loss_sum, float* logits, int Q, int C, int d,

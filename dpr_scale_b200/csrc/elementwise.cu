@@ -69,7 +69,7 @@ ln_fwd_kernel(const bf16* __restrict__ z, const int64_t* __restrict__ ids, const
               const int64_t* __restrict__ pids, const float* __restrict__ word, const float* __restrict__ pos,
               const float* __restrict__ type, const float* __restrict__ gamma, const float* __restrict__ beta,
               bf16* __restrict__ y, float* __restrict__ stats, float* __restrict__ cls_out, int cls_stride, int T,
-              int H, float eps) {
+              int H, float eps, Drop drop) {
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * WARPS + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * WARPS;
@@ -119,6 +119,10 @@ ln_fwd_kernel(const bf16* __restrict__ z, const int64_t* __restrict__ ids, const
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = (x[i][j] - mean) * rstd * g[i][j] + b[i][j];
+        if (EMBED && drop.on()) {  // embedding dropout (modeling_bert.py:111)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] *= drop.mul((uint64_t)row * H + c + j);
+        }
         store8(y + (long long)row * H + c, o);
         if (is_cls) store8f(cls_out + (long long)(row / cls_stride) * H + c, o);
       }
@@ -158,7 +162,8 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ dy_cls, int
               const int64_t* __restrict__ pids, const float* __restrict__ word, const float* __restrict__ pos,
               const float* __restrict__ type, const float* __restrict__ stats, const float* __restrict__ gamma,
               bf16* __restrict__ dz, float* __restrict__ dword, float* __restrict__ dpos, float* __restrict__ dtype,
-              float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int T, int H) {
+              float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int T, int H,
+              bf16* __restrict__ dzm, Drop drop) {
   extern __shared__ float smem_f[];
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * WARPS + (threadIdx.x >> 5);
@@ -250,6 +255,10 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ dy_cls, int
         if (sparse_dy) load8f(dy_cls + (long long)(row / cls_stride) * H + c, d[i]);
         else if (dense_path) unpack8(cdy[i], d[i]);
         else load8(dy + (long long)row * H + c, d[i]);
+        if (EMBED && drop.on()) {  // upstream gradient is w.r.t. the dropped embedding output
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[i][j] *= drop.mul((uint64_t)row * H + c + j);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           xh[i][j] = (x[j] - mean) * rstd;
@@ -282,6 +291,13 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ dy_cls, int
           }
         } else {
           store8(dz + (long long)row * H + c, o);
+          if (dzm != nullptr) {
+            // hidden dropout sat between the Linear and this residual+LayerNorm: the Linear's output gradient is
+            // dz * mask / (1-p) (second output), while the residual branch takes dz itself
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] *= drop.mul((uint64_t)row * H + c + j);
+            store8(dzm + (long long)row * H + c, o);
+          }
           if (dbias != nullptr) {
             // accumulate the bf16-rounded value: it is what the downstream GEMMs consume
 #pragma unroll
@@ -355,12 +371,14 @@ static int check_h(int H, const char* who) {
 
 int embed_ln_fwd(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, const float* word,
                  const float* pos, const float* type, const float* gamma, const float* beta, void* y, float* stats,
-                 int T, int H, int vocab, int max_pos, int type_vocab, float eps, cudaStream_t stream) {
+                 int T, int H, int vocab, int max_pos, int type_vocab, float eps, float dropout_p,
+                 unsigned long long seed, cudaStream_t stream) {
+  const Drop drop = make_drop(dropout_p, seed, 0, DROP_SITE_EMBED);
   if (int rc = check_h(H, "embed_ln_fwd")) return rc;
   if (T == 0) return 0;
   (void)vocab; (void)max_pos; (void)type_vocab;
   const int grid = grid_for_rows(T);
-#define CALL(C) ln_fwd_kernel<C, true><<<grid, THREADS, 0, stream>>>(nullptr, ids, type_ids, pos_ids, word, pos, type, gamma, beta, (bf16*)y, stats, nullptr, 1, T, H, eps)
+#define CALL(C) ln_fwd_kernel<C, true><<<grid, THREADS, 0, stream>>>(nullptr, ids, type_ids, pos_ids, word, pos, type, gamma, beta, (bf16*)y, stats, nullptr, 1, T, H, eps, drop)
   DISPATCH_MAXC(H, CALL);
 #undef CALL
   DPRB_CHECK_CUDA(cudaGetLastError());
@@ -373,7 +391,7 @@ int ln_fwd(const void* z, const float* gamma, const float* beta, void* y, float*
   if (T == 0) return 0;
   DPRB_REQUIRE(cls_out == nullptr || cls_stride > 0, "ln_fwd: cls_stride must be positive");
   const int grid = grid_for_rows(T);
-#define CALL(C) ln_fwd_kernel<C, false><<<grid, THREADS, 0, stream>>>((const bf16*)z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, gamma, beta, (bf16*)y, stats, cls_out, cls_stride > 0 ? cls_stride : 1, T, H, eps)
+#define CALL(C) ln_fwd_kernel<C, false><<<grid, THREADS, 0, stream>>>((const bf16*)z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, gamma, beta, (bf16*)y, stats, cls_out, cls_stride > 0 ? cls_stride : 1, T, H, eps, Drop{0, 0, 1.f})
   DISPATCH_MAXC(H, CALL);
 #undef CALL
   DPRB_CHECK_CUDA(cudaGetLastError());
@@ -381,8 +399,11 @@ int ln_fwd(const void* z, const float* gamma, const float* beta, void* y, float*
 }
 
 int ln_bwd(const void* dy, const float* dy_cls, int cls_stride, const void* z, const float* stats,
-           const float* gamma, void* dz, float* dgamma, float* dbeta, float* dbias, int T, int H,
-           cudaStream_t stream) {
+           const float* gamma, void* dz, float* dgamma, float* dbeta, float* dbias, int T, int H, void* dzm,
+           float dropout_p, unsigned long long site_seed, cudaStream_t stream) {
+  Drop drop = make_drop(dropout_p, 0, 0, 0);
+  drop.seed = site_seed;  // the caller passes the fully derived site seed
+  if (!drop.on()) dzm = nullptr;
   if (int rc = check_h(H, "ln_bwd")) return rc;
   if (T == 0) return 0;
   DPRB_REQUIRE((dy != nullptr) != (dy_cls != nullptr), "ln_bwd: exactly one of dy / dy_cls must be given");
@@ -400,7 +421,7 @@ int ln_bwd(const void* dy, const float* dy_cls, int cls_stride, const void* z, c
     DPRB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr = true;
   }
-#define CALL(C) ln_bwd_kernel<C, false><<<grid, THREADS, smem, stream>>>((const bf16*)dy, dy_cls, cls_stride > 0 ? cls_stride : 1, (const bf16*)z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stats, gamma, (bf16*)dz, nullptr, nullptr, nullptr, dgamma, dbeta, dbias, T, H)
+#define CALL(C) ln_bwd_kernel<C, false><<<grid, THREADS, smem, stream>>>((const bf16*)dy, dy_cls, cls_stride > 0 ? cls_stride : 1, (const bf16*)z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stats, gamma, (bf16*)dz, nullptr, nullptr, nullptr, dgamma, dbeta, dbias, T, H, (bf16*)dzm, drop)
   DISPATCH_MAXC(H, CALL);
 #undef CALL
   DPRB_CHECK_CUDA(cudaGetLastError());
@@ -410,14 +431,29 @@ int ln_bwd(const void* dy, const float* dy_cls, int cls_stride, const void* z, c
 int embed_ln_bwd(const void* dy, const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids,
                  const float* word, const float* pos, const float* type, const float* gamma, const float* stats,
                  float* dword, float* dpos, float* dtype, float* dgamma, float* dbeta, int T, int H,
-                 cudaStream_t stream) {
+                 float dropout_p, unsigned long long seed, cudaStream_t stream) {
+  const Drop drop = make_drop(dropout_p, seed, 0, DROP_SITE_EMBED);
   if (int rc = check_h(H, "embed_ln_bwd")) return rc;
   if (T == 0) return 0;
   const int grid = grid_for_rows(T);
   const size_t smem = (size_t)WARPS * H * sizeof(float);
-#define CALL(C) ln_bwd_kernel<C, true><<<grid, THREADS, smem, stream>>>((const bf16*)dy, nullptr, 1, nullptr, ids, type_ids, pos_ids, word, pos, type, stats, gamma, nullptr, dword, dpos, dtype, dgamma, dbeta, nullptr, T, H)
+#define CALL(C) ln_bwd_kernel<C, true><<<grid, THREADS, smem, stream>>>((const bf16*)dy, nullptr, 1, nullptr, ids, type_ids, pos_ids, word, pos, type, stats, gamma, nullptr, dword, dpos, dtype, dgamma, dbeta, nullptr, T, H, nullptr, drop)
   DISPATCH_MAXC(H, CALL);
 #undef CALL
+  DPRB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void dropout_mask_kernel(uint8_t* out, long long n, Drop drop) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = drop.on() ? (uint8_t)dropout_keep((uint64_t)i, drop.seed, drop.thresh) : (uint8_t)1;
+}
+
+// Test aid: materialise the keep mask of one dropout site (the kernels never store masks).
+int dropout_mask(uint8_t* out, long long n, float p, unsigned long long seed, int layer, int site, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  const Drop d = make_drop(p, seed, layer, site);
+  dropout_mask_kernel<<<(int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, stream>>>(out, n, d);
   DPRB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -33,7 +33,7 @@ struct Workspace {
   int n_layer_slots;
   LayerActs slot[64];
   // backward scratch
-  bf16 *gA, *gB, *gH, *gQKV;
+  bf16 *gA, *gB, *gB2, *gH, *gQKV;
   long long bytes;
 };
 
@@ -63,10 +63,11 @@ int plan(const dprb_encoder_weights* w, int nseq, int S, int save, void* base, W
   if (save) {
     ws->gA = (bf16*)c.take(T * H * 2);
     ws->gB = (bf16*)c.take(T * H * 2);
+    ws->gB2 = (bf16*)c.take(T * H * 2);  // dz * mask/(1-p): the Linear-side gradient when hidden dropout is on
     ws->gH = (bf16*)c.take(T * I * 2);
     ws->gQKV = (bf16*)c.take(T * 3 * H * 2);
   } else {
-    ws->gA = ws->gB = ws->gH = ws->gQKV = nullptr;
+    ws->gA = ws->gB = ws->gB2 = ws->gH = ws->gQKV = nullptr;
   }
   ws->bytes = c.off;
   return 0;
@@ -95,6 +96,10 @@ LayerW layer_w(const dprb_encoder_weights* w, int l) {
   return r;
 }
 
+unsigned long long site_seed(const dprb_encoder_batch* b, int layer, int site) {
+  return make_drop(b->dropout_p, b->dropout_seed, layer, site).seed;
+}
+
 #define TRY(expr) do { if (int _rc = (expr)) return _rc; } while (0)
 
 }  // namespace
@@ -116,17 +121,19 @@ int encoder_fwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b, floa
   const float* ms = w->master;
   TRY(embed_ln_fwd(b->ids, b->type_ids, b->pos_ids, ms + w->off_word, ms + w->off_pos, ms + w->off_type,
                    ms + w->off_emb_ln_g, ms + w->off_emb_ln_b, ws.x0, ws.emb_stats, T, H, w->vocab, w->max_pos,
-                   w->type_vocab, w->ln_eps, stream));
+                   w->type_vocab, w->ln_eps, b->dropout_p, b->dropout_seed, stream));
   const bf16* x = ws.x0;
+  const float dp = b->dropout_p;
+  DPRB_REQUIRE(dp >= 0.f && dp < 1.f, "encoder_fwd: dropout_p %f out of range", dp);
   for (int l = 0; l < L; ++l) {
     const LayerW lw = layer_w(w, l);
     LayerActs& a = ws.slot[b->save_for_backward ? l : (l & 1)];
-    TRY(gemm_bf16(x, lw.wqkv, a.qkv, T, 3 * H, H, H, H, 3 * H, 0, 0, DPRB_EPI_BIAS, lw.bqkv, nullptr, 0, nullptr, 1.f, 1, nullptr, stream));
-    TRY(attn_fwd_lse(a.qkv, b->attn_mask, a.ctx, a.lse, b->nseq, b->S, w->heads, stream));
-    TRY(gemm_bf16(a.ctx, lw.wo, a.z1, T, H, H, H, H, H, 0, 0, DPRB_EPI_BIAS_RESIDUAL, lw.bo, x, H, nullptr, 1.f, 1, nullptr, stream));
+    TRY(gemm_bf16(x, lw.wqkv, a.qkv, T, 3 * H, H, H, H, 3 * H, 0, 0, DPRB_EPI_BIAS, lw.bqkv, nullptr, 0, nullptr, 1.f, 1, nullptr, 0.f, 0, stream));
+    TRY(attn_fwd_lse(a.qkv, b->attn_mask, a.ctx, a.lse, b->nseq, b->S, w->heads, dp, site_seed(b, l, DROP_SITE_ATTN), stream));
+    TRY(gemm_bf16(a.ctx, lw.wo, a.z1, T, H, H, H, H, H, 0, 0, DPRB_EPI_BIAS_RESIDUAL, lw.bo, x, H, nullptr, 1.f, 1, nullptr, dp, site_seed(b, l, DROP_SITE_ATTN_OUT), stream));
     TRY(ln_fwd(a.z1, lw.ln1g, lw.ln1b, a.x1, a.stats1, nullptr, 1, T, H, w->ln_eps, stream));
-    TRY(gemm_bf16(a.x1, lw.w1, a.hact, T, I, H, H, H, I, 0, 0, DPRB_EPI_BIAS_GELU, lw.b1, nullptr, 0, a.hpre, 1.f, 1, nullptr, stream));
-    TRY(gemm_bf16(a.hact, lw.w2, a.z2, T, H, I, I, I, H, 0, 0, DPRB_EPI_BIAS_RESIDUAL, lw.b2, a.x1, H, nullptr, 1.f, 1, nullptr, stream));
+    TRY(gemm_bf16(a.x1, lw.w1, a.hact, T, I, H, H, H, I, 0, 0, DPRB_EPI_BIAS_GELU, lw.b1, nullptr, 0, a.hpre, 1.f, 1, nullptr, 0.f, 0, stream));
+    TRY(gemm_bf16(a.hact, lw.w2, a.z2, T, H, I, I, I, H, 0, 0, DPRB_EPI_BIAS_RESIDUAL, lw.b2, a.x1, H, nullptr, 1.f, 1, nullptr, dp, site_seed(b, l, DROP_SITE_FFN_OUT), stream));
     const bool last = (l == L - 1);
     TRY(ln_fwd(a.z2, lw.ln2g, lw.ln2b, a.out, a.stats2, last ? pooled : nullptr, b->S, T, H, w->ln_eps, stream));
     x = a.out;
@@ -149,37 +156,42 @@ int encoder_bwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b, cons
     LayerActs& a = ws.slot[l];
     const bf16* x = (l == 0) ? ws.x0 : ws.slot[l - 1].out;
     const bool last = (l == L - 1);
+    const float dp = b->dropout_p;
+    // with hidden dropout the Linear-side gradient is dz * mask/(1-p) (gB2); the residual branch keeps dz (gB)
+    const bf16* gLin = dp > 0.f ? ws.gB2 : ws.gB;
     // LN2 backward (+ db2)
     TRY(ln_bwd(last ? nullptr : ws.gA, last ? dpooled : nullptr, b->S, a.z2, a.stats2, lw.ln2g, ws.gB, lw.g_ln2g,
-               lw.g_ln2b, lw.g_b2, T, H, stream));
+               lw.g_ln2b, lw.g_b2, T, H, ws.gB2, dp, site_seed(b, l, DROP_SITE_FFN_OUT), stream));
     // dW2 += dz2^T hact
-    TRY(gemm_bf16(ws.gB, a.hact, lw.g_w2, H, I, T, H, I, I, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, stream));
+    TRY(gemm_bf16(gLin, a.hact, lw.g_w2, H, I, T, H, I, I, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, 0.f, 0, stream));
     // dhpre = (dz2 W2) * gelu'(hpre)
-    TRY(gemm_bf16(ws.gB, lw.w2, ws.gH, T, I, H, H, I, I, 0, 1, DPRB_EPI_DGELU, nullptr, a.hpre, I, nullptr, 1.f, 1, lw.g_b1, stream));
+    TRY(gemm_bf16(gLin, lw.w2, ws.gH, T, I, H, H, I, I, 0, 1, DPRB_EPI_DGELU, nullptr, a.hpre, I, nullptr, 1.f, 1, lw.g_b1, 0.f, 0, stream));
     // (db1 = column sums of dhpre is fused into that epilogue: +58 us vs 129 us for a separate streaming pass)
     // dW1 += dhpre^T x1
-    TRY(gemm_bf16(ws.gH, a.x1, lw.g_w1, I, H, T, I, H, H, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, stream));
+    TRY(gemm_bf16(ws.gH, a.x1, lw.g_w1, I, H, T, I, H, H, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, 0.f, 0, stream));
     // dx1 = dhpre W1 + dz2
-    TRY(gemm_bf16(ws.gH, lw.w1, ws.gA, T, H, I, I, H, H, 0, 1, DPRB_EPI_BIAS_RESIDUAL, nullptr, ws.gB, H, nullptr, 1.f, 1, nullptr, stream));
+    TRY(gemm_bf16(ws.gH, lw.w1, ws.gA, T, H, I, I, H, H, 0, 1, DPRB_EPI_BIAS_RESIDUAL, nullptr, ws.gB, H, nullptr, 1.f, 1, nullptr, 0.f, 0, stream));
     // LN1 backward (+ dbo)
-    TRY(ln_bwd(ws.gA, nullptr, 1, a.z1, a.stats1, lw.ln1g, ws.gB, lw.g_ln1g, lw.g_ln1b, lw.g_bo, T, H, stream));
+    TRY(ln_bwd(ws.gA, nullptr, 1, a.z1, a.stats1, lw.ln1g, ws.gB, lw.g_ln1g, lw.g_ln1b, lw.g_bo, T, H, ws.gB2, dp,
+               site_seed(b, l, DROP_SITE_ATTN_OUT), stream));
     // dWo += dz1^T ctx
-    TRY(gemm_bf16(ws.gB, a.ctx, lw.g_wo, H, H, T, H, H, H, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, stream));
+    TRY(gemm_bf16(gLin, a.ctx, lw.g_wo, H, H, T, H, H, H, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, 0.f, 0, stream));
     // dctx = dz1 Wo
-    TRY(gemm_bf16(ws.gB, lw.wo, ws.gA, T, H, H, H, H, H, 0, 1, DPRB_EPI_BIAS, nullptr, nullptr, 0, nullptr, 1.f, 1, nullptr, stream));
+    TRY(gemm_bf16(gLin, lw.wo, ws.gA, T, H, H, H, H, H, 0, 1, DPRB_EPI_BIAS, nullptr, nullptr, 0, nullptr, 1.f, 1, nullptr, 0.f, 0, stream));
     // (+ dbqkv: column sums of dqkv fused into the attention-backward epilogue)
-    TRY(attn_bwd_lse(a.qkv, b->attn_mask, a.ctx, a.lse, ws.gA, ws.gQKV, lw.g_bqkv, b->nseq, b->S, w->heads, stream));
+    TRY(attn_bwd_lse(a.qkv, b->attn_mask, a.ctx, a.lse, ws.gA, ws.gQKV, lw.g_bqkv, b->nseq, b->S, w->heads, dp,
+                     site_seed(b, l, DROP_SITE_ATTN), stream));
     // dWqkv += dqkv^T x
-    TRY(gemm_bf16(ws.gQKV, x, lw.g_wqkv, 3 * H, H, T, 3 * H, H, H, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, stream));
+    TRY(gemm_bf16(ws.gQKV, x, lw.g_wqkv, 3 * H, H, T, 3 * H, H, H, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, 0.f, 0, stream));
     // dx = dqkv Wqkv + dz1
-    TRY(gemm_bf16(ws.gQKV, lw.wqkv, ws.gA, T, H, 3 * H, 3 * H, H, H, 0, 1, DPRB_EPI_BIAS_RESIDUAL, nullptr, ws.gB, H, nullptr, 1.f, 1, nullptr, stream));
+    TRY(gemm_bf16(ws.gQKV, lw.wqkv, ws.gA, T, H, 3 * H, 3 * H, H, H, 0, 1, DPRB_EPI_BIAS_RESIDUAL, nullptr, ws.gB, H, nullptr, 1.f, 1, nullptr, 0.f, 0, stream));
   }
   if (layer_lo == 0) {
     const float* ms = w->master;
     float* gr = w->grads;
     TRY(embed_ln_bwd(ws.gA, b->ids, b->type_ids, b->pos_ids, ms + w->off_word, ms + w->off_pos, ms + w->off_type,
                      ms + w->off_emb_ln_g, ws.emb_stats, gr + w->off_word, gr + w->off_pos, gr + w->off_type,
-                     gr + w->off_emb_ln_g, gr + w->off_emb_ln_b, T, H, stream));
+                     gr + w->off_emb_ln_g, gr + w->off_emb_ln_b, T, H, b->dropout_p, b->dropout_seed, stream));
   }
   return 0;
 }

@@ -65,6 +65,7 @@ struct GemmParams {
   float alpha;         // scale applied to the accumulator before the epilogue
   float* colsum;       // optional: colsum[n] += sum_m D(m, n) of the bf16-rounded output (bias gradients)
   int aux_prefetch;    // 1: request aux with cp.async before waiting for the accumulator (CG = 2 only)
+  Drop drop;           // EPI_BIAS_RESIDUAL only: D = dropout(acc + bias) + aux  (hidden dropout before the residual)
 };
 
 // ---- cluster / 2-CTA helpers -------------------------------------------------------------------------------
@@ -449,8 +450,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const float a[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
-                  if (p.epilogue == DPRB_EPI_BIAS_RESIDUAL) v[c4 * 8 + t] += a[t];
-                  else v[c4 * 8 + t] *= gelu_erf_grad(a[t]);
+                  if (p.epilogue == DPRB_EPI_BIAS_RESIDUAL) {
+                    if (p.drop.on()) v[c4 * 8 + t] *= p.drop.mul((uint64_t)row * p.N + col0 + c4 * 8 + t);
+                    v[c4 * 8 + t] += a[t];
+                  } else {
+                    v[c4 * 8 + t] *= gelu_erf_grad(a[t]);
+                  }
                 }
               }
             }
@@ -572,7 +577,8 @@ int choose_splits(int tiles, int k_blocks, int sms) {
 
 int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long long lda, long long ldb,
               long long ldd, int a_mn_major, int b_mn_major, int epilogue, const float* bias, const void* aux,
-              long long ld_aux, void* out2, float alpha, int splits, float* colsum, cudaStream_t stream) {
+              long long ld_aux, void* out2, float alpha, int splits, float* colsum, float dropout_p,
+              unsigned long long drop_site_seed, cudaStream_t stream) {
   DPRB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   DPRB_REQUIRE(epilogue >= 0 && epilogue < DPRB_EPI_COUNT, "gemm: bad epilogue %d", epilogue);
   const bool f32_out = (epilogue == DPRB_EPI_F32_ATOMIC_ADD || epilogue == DPRB_EPI_F32_STORE);
@@ -624,6 +630,8 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long l
   p.D = D; p.ldd = ldd; p.bias = bias; p.aux = reinterpret_cast<const bf16*>(aux); p.ld_aux = ld_aux;
   p.out2 = reinterpret_cast<bf16*>(out2); p.alpha = alpha;
   p.colsum = colsum;
+  p.drop = make_drop(epilogue == DPRB_EPI_BIAS_RESIDUAL ? dropout_p : 0.f, 0, 0, 0);
+  p.drop.seed = drop_site_seed;
   static const bool no_aux_pf = (std::getenv("DPRB_NO_AUX_PF") != nullptr);
   // measured (same box, cfg-2 shapes): prefetching aux before the accumulator wait gains 10-14 % where the epilogue
   // is the critical path (K <= 1024: attention-out, dGELU) and costs ~1.5 % on the K >= 2304 GEMMs

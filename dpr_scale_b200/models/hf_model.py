@@ -212,6 +212,8 @@ class HFEncoder(nn.Module):
         # flat arena overlaps with the rest of backward.
         self.grad_sync = None
         self.bwd_chunk_layers = 0
+        self._drop_base = (torch.initial_seed() * 0x9E3779B97F4A7C15 + id(self)) & 0xFFFFFFFFFFFFFFFF
+        self._drop_calls = 0
 
     # ------------------------------------------------------------------ construction helpers
     @classmethod
@@ -367,6 +369,11 @@ class HFEncoder(nn.Module):
         b.attn_mask = am.data_ptr() if am is not None else None
         b.workspace, b.workspace_bytes = base, ws.numel() - (base - ws.data_ptr())
         b.save_for_backward = int(save)
+        # HF applies dropout only in train mode; the seed changes every forward and is replayed by backward
+        b.dropout_p = self.dropout if (self.training and save) else 0.0
+        self._drop_calls += 1
+        b.dropout_seed = (self._drop_base + self._drop_calls * 0x2545F4914F6CDD1D) & 0xFFFFFFFFFFFFFFFF
+        self.last_dropout = (float(b.dropout_p), int(b.dropout_seed))  # exposed for tests (mask reconstruction)
         w = self._weights_struct(save)
         pooled = torch.empty(N, self.config["hidden_size"], dtype=torch.float32, device=ids.device)
         stream = torch.cuda.current_stream().cuda_stream
@@ -398,10 +405,6 @@ class HFEncoder(nn.Module):
                 self.grad_sync(self, e_lo, lay.off_layer0 + hi * lay.layer_stride)
 
     def forward(self, tokens):
-        if self.training and self.dropout > 0.0 and not self._warned_dropout:
-            warnings.warn("dprb HFEncoder: dropout>0 requested; the sm_100a kernels of this round run without "
-                          "dropout (deterministic). Set dropout=0 to silence.", RuntimeWarning)
-            self._warned_dropout = True
         save = torch.is_grad_enabled()
         if save:
             # any arena parameter works as the autograd anchor; gradients are written by the kernels

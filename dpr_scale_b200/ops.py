@@ -30,11 +30,11 @@ def _stream():
 
 
 def gemm(a, b, out, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, epilogue=EPI_BIAS, bias=None, aux=None,
-         ld_aux=0, out2=None, alpha=1.0, splits=1, colsum=None):
+         ld_aux=0, out2=None, alpha=1.0, splits=1, colsum=None, dropout_p=0.0, drop_seed=0):
     lib = _lib.load()
     check(lib.dprb_gemm_bf16(_ptr(a), _ptr(b), _ptr(out), M, N, K, lda, ldb, ldd, int(a_mn), int(b_mn), epilogue,
                              _ptr(bias), _ptr(aux), ld_aux, _ptr(out2), float(alpha), splits, _ptr(colsum),
-                             _stream()),
+                             float(dropout_p), int(drop_seed), _stream()),
           "dprb_gemm_bf16")
     _count()
     return out
@@ -49,24 +49,27 @@ def linear_fwd(x, w, bias=None, epilogue=EPI_BIAS, aux=None, out2=None):
     return y
 
 
-def embed_ln_fwd(ids, type_ids, pos_ids, word, pos, typ, gamma, beta, eps):
+def embed_ln_fwd(ids, type_ids, pos_ids, word, pos, typ, gamma, beta, eps, dropout_p=0.0, seed=0):
     T = ids.numel()
     H = word.shape[1]
     y = torch.empty(T, H, dtype=torch.bfloat16, device=word.device)
     stats = torch.empty(T, 2, dtype=torch.float32, device=word.device)
     check(_lib.load().dprb_embed_ln_fwd(_ptr(ids), _ptr(type_ids), _ptr(pos_ids), _ptr(word), _ptr(pos), _ptr(typ),
                                         _ptr(gamma), _ptr(beta), _ptr(y), _ptr(stats), T, H, word.shape[0],
-                                        pos.shape[0], typ.shape[0], float(eps), _stream()), "dprb_embed_ln_fwd")
+                                        pos.shape[0], typ.shape[0], float(eps), float(dropout_p), int(seed),
+                                        _stream()), "dprb_embed_ln_fwd")
     _count()
     return y, stats
 
 
-def embed_ln_bwd(dy, ids, type_ids, pos_ids, word, pos, typ, gamma, stats, dword, dpos, dtyp, dgamma, dbeta):
+def embed_ln_bwd(dy, ids, type_ids, pos_ids, word, pos, typ, gamma, stats, dword, dpos, dtyp, dgamma, dbeta,
+                 dropout_p=0.0, seed=0):
     T = ids.numel()
     H = word.shape[1]
     check(_lib.load().dprb_embed_ln_bwd(_ptr(dy), _ptr(ids), _ptr(type_ids), _ptr(pos_ids), _ptr(word), _ptr(pos),
                                         _ptr(typ), _ptr(gamma), _ptr(stats), _ptr(dword), _ptr(dpos), _ptr(dtyp),
-                                        _ptr(dgamma), _ptr(dbeta), T, H, _stream()), "dprb_embed_ln_bwd")
+                                        _ptr(dgamma), _ptr(dbeta), T, H, float(dropout_p), int(seed), _stream()),
+          "dprb_embed_ln_bwd")
     _count()
 
 
@@ -83,13 +86,26 @@ def ln_fwd(z, gamma, beta, eps, cls_stride=0):
     return y, stats, cls
 
 
-def ln_bwd(dy, z, stats, gamma, dgamma, dbeta, dbias=None, dy_cls=None, cls_stride=1):
+def ln_bwd(dy, z, stats, gamma, dgamma, dbeta, dbias=None, dy_cls=None, cls_stride=1, dropout_p=0.0, site_seed=0):
     T, H = z.shape
     dz = torch.empty_like(z)
+    dzm = torch.empty_like(z) if dropout_p > 0 else None
     check(_lib.load().dprb_ln_bwd(_ptr(dy), _ptr(dy_cls), cls_stride, _ptr(z), _ptr(stats), _ptr(gamma), _ptr(dz),
-                                  _ptr(dgamma), _ptr(dbeta), _ptr(dbias), T, H, _stream()), "dprb_ln_bwd")
+                                  _ptr(dgamma), _ptr(dbeta), _ptr(dbias), T, H, _ptr(dzm), float(dropout_p),
+                                  int(site_seed), _stream()), "dprb_ln_bwd")
     _count()
-    return dz
+    return (dz, dzm) if dropout_p > 0 else dz
+
+
+def dropout_site_seed(seed, layer, site):
+    return int(_lib.load().dprb_dropout_site_seed(int(seed), layer, site))
+
+
+def dropout_mask(n, p, seed, layer, site, device="cuda"):
+    """keep mask (uint8) of one dropout site for flat element indices [0, n) — test aid."""
+    out = torch.empty(n, dtype=torch.uint8, device=device)
+    check(_lib.load().dprb_dropout_mask(_ptr(out), n, float(p), int(seed), layer, site, _stream()), "dprb_dropout_mask")
+    return out
 
 
 def colsum(x, out):
@@ -99,21 +115,22 @@ def colsum(x, out):
     return out
 
 
-def attn_fwd(qkv, attn_mask, nseq, S, heads, need_lse=True):
+def attn_fwd(qkv, attn_mask, nseq, S, heads, need_lse=True, dropout_p=0.0, site_seed=0):
     T = nseq * S
     H = heads * 64
     ctx = torch.empty(T, H, dtype=torch.bfloat16, device=qkv.device)
     lse = torch.empty(nseq, heads, S, dtype=torch.float32, device=qkv.device) if need_lse else None
-    check(_lib.load().dprb_attn_fwd(_ptr(qkv), _ptr(attn_mask), _ptr(ctx), _ptr(lse), nseq, S, heads, _stream()),
-          "dprb_attn_fwd")
+    check(_lib.load().dprb_attn_fwd(_ptr(qkv), _ptr(attn_mask), _ptr(ctx), _ptr(lse), nseq, S, heads, float(dropout_p),
+                                    int(site_seed), _stream()), "dprb_attn_fwd")
     _count()
     return ctx, lse
 
 
-def attn_bwd(qkv, attn_mask, ctx, lse, dctx, nseq, S, heads, dbias=None):
+def attn_bwd(qkv, attn_mask, ctx, lse, dctx, nseq, S, heads, dbias=None, dropout_p=0.0, site_seed=0):
     dqkv = torch.empty_like(qkv)
     check(_lib.load().dprb_attn_bwd(_ptr(qkv), _ptr(attn_mask), _ptr(ctx), _ptr(lse), _ptr(dctx), _ptr(dqkv),
-                                    _ptr(dbias), nseq, S, heads, _stream()), "dprb_attn_bwd")
+                                    _ptr(dbias), nseq, S, heads, float(dropout_p), int(site_seed), _stream()),
+          "dprb_attn_bwd")
     _count()
     return dqkv
 

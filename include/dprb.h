@@ -39,6 +39,9 @@ int dprb_num_sms(void);
  *   [3H,H] weight), :295 (attention output dense), :340 (intermediate dense), :353 (output dense).
  * colsum (optional, bf16 epilogues except BIAS_GELU): colsum[n] += sum_m D(m,n) — the bias gradient of the
  * Linear whose output gradient this GEMM produces, fused into the epilogue instead of a separate pass.
+ * dropout_p / dropout_site_seed (BIAS_RESIDUAL only): D = dropout(acc + bias) + aux — HF's hidden dropout between the
+ * dense layer and the residual add (modeling_bert.py:296-297, :354-355); the mask is a counter-based hash of the
+ * element index (never stored; dprb_ln_bwd re-derives it, dprb_dropout_mask exports it for tests).
  * a_mn_major/b_mn_major = 0: operand stored [MN, K] (K contiguous, leading dim ld);
  *                       = 1: operand stored [K, MN] (MN contiguous, leading dim ld).
  * ------------------------------------------------------------------------------------------- */
@@ -54,7 +57,7 @@ enum {
 int dprb_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int64_t lda, int64_t ldb,
                    int64_t ldd, int a_mn_major, int b_mn_major, int epilogue, const float* bias,
                    const void* aux, int64_t ld_aux, void* out2, float alpha, int splits, float* colsum,
-                   dprb_stream_t stream);
+                   float dropout_p, uint64_t dropout_site_seed, dprb_stream_t stream);
 
 /* Measurement aid (bench.py roofline leg): when enabled, every GEMM launch is bracketed by CUDA events on
  * its launch stream; dprb_gemm_profile_read sums the per-launch durations and algorithmic FLOPs (2*M*N*K). */
@@ -69,12 +72,12 @@ int dprb_gemm_profile_read(double* total_ms, double* total_flops, int64_t* launc
 int dprb_embed_ln_fwd(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, const float* word,
                       const float* pos, const float* type, const float* gamma, const float* beta, void* y_bf16,
                       float* stats, int T, int H, int vocab, int max_pos, int type_vocab, float eps,
-                      dprb_stream_t stream);
+                      float dropout_p, uint64_t dropout_seed, dprb_stream_t stream);
 /* Backward: dz = LN'(dy); dgamma/dbeta accumulated; scatter-add of dz into the three table grads. */
 int dprb_embed_ln_bwd(const void* dy_bf16, const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids,
                       const float* word, const float* pos, const float* type, const float* gamma,
                       const float* stats, float* dword, float* dpos, float* dtype, float* dgamma, float* dbeta,
-                      int T, int H, dprb_stream_t stream);
+                      int T, int H, float dropout_p, uint64_t dropout_seed, dprb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * LayerNorm over rows of z (the residual sum is produced by the preceding GEMM epilogue).
@@ -87,9 +90,18 @@ int dprb_ln_fwd(const void* z_bf16, const float* gamma, const float* beta, void*
 /* dz = LN'(dy; z, stats); dgamma += sum dy*xhat; dbeta += sum dy; if dbias != NULL: dbias += sum_t dz
  * (the bias gradient of the Linear that produced z).  If dy_cls != NULL, dy is implicit: zero
  * everywhere except rows t % cls_stride == 0 which take dy_cls[t / cls_stride, :] (fp32). */
+/* With hidden dropout (dropout_p > 0): dzm_bf16 receives dz * mask/(1-p) — the gradient of the Linear output that was
+ * dropped before the residual add — and dbias sums dzm instead of dz. */
 int dprb_ln_bwd(const void* dy_bf16, const float* dy_cls, int cls_stride, const void* z_bf16,
                 const float* stats, const float* gamma, void* dz_bf16, float* dgamma, float* dbeta,
-                float* dbias, int T, int H, dprb_stream_t stream);
+                float* dbias, int T, int H, void* dzm_bf16, float dropout_p, uint64_t dropout_site_seed,
+                dprb_stream_t stream);
+/* Dropout sites: 0 embeddings, 1 attention probabilities, 2 attention-output dense, 3 FFN-output dense.
+ * site seed = dropout_seed + (layer*8 + site + 1) * 0x9E3779B97F4A7C15 (mod 2^64).
+ * dprb_dropout_mask materialises keep[i] for element indices i in [0, n) of one site (test aid). */
+uint64_t dprb_dropout_site_seed(uint64_t dropout_seed, int layer, int site);
+int dprb_dropout_mask(uint8_t* keep, int64_t n, float dropout_p, uint64_t dropout_seed, int layer, int site,
+                      dprb_stream_t stream);
 
 /* Column sums: out[n] += sum_t x[t, n]  (bias gradients; x bf16 [T, N] with leading dim ld). */
 int dprb_colsum_bf16(const void* x_bf16, int64_t ld, float* out, int T, int N, dprb_stream_t stream);
@@ -104,11 +116,11 @@ int dprb_colsum_bf16(const void* x_bf16, int64_t ld, float* out, int T, int N, d
  *      forward-only use) and consumed by bwd together with the forward output ctx.
  * ------------------------------------------------------------------------------------------- */
 int dprb_attn_fwd(const void* qkv_bf16, const int32_t* attn_mask, void* ctx_bf16, float* lse, int nseq, int S,
-                  int heads, dprb_stream_t stream);
+                  int heads, float dropout_p, uint64_t dropout_site_seed, dprb_stream_t stream);
 /* dbias (optional, fp32 [3H]): dbias[n] += sum_t dqkv[t, n] — the bias gradient of the fused QKV projection. */
 int dprb_attn_bwd(const void* qkv_bf16, const int32_t* attn_mask, const void* ctx_bf16, const float* lse,
                   const void* dctx_bf16, void* dqkv_bf16, float* dbias, int nseq, int S, int heads,
-                  dprb_stream_t stream);
+                  float dropout_p, uint64_t dropout_site_seed, dprb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused in-batch-negative scoring + softmax cross-entropy.
@@ -174,6 +186,8 @@ typedef struct {
   void* workspace;
   int64_t workspace_bytes;
   int32_t save_for_backward; /* 0: forward-only (generate_embeddings path) reuses per-layer buffers */
+  float dropout_p;           /* hidden + attention-probability dropout (HFEncoder's `dropout`); 0 in eval mode */
+  uint64_t dropout_seed;     /* per-forward seed; backward must be given the same value */
 } dprb_encoder_batch;
 
 int64_t dprb_encoder_workspace_bytes(const dprb_encoder_weights* w, int nseq, int S, int save_for_backward);

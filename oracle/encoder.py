@@ -30,14 +30,15 @@ def gelu_erf(x):
     return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
 
 
-def embeddings(sd, pfx, input_ids, token_type_ids, position_ids, eps):
+def embeddings(sd, pfx, input_ids, token_type_ids, position_ids, eps, drop=None):
     e = sd[pfx + "embeddings.word_embeddings.weight"][input_ids]
     e = e + sd[pfx + "embeddings.token_type_embeddings.weight"][token_type_ids]
     e = e + sd[pfx + "embeddings.position_embeddings.weight"][position_ids]
-    return layer_norm(e, sd[pfx + "embeddings.LayerNorm.weight"], sd[pfx + "embeddings.LayerNorm.bias"], eps)
+    y = layer_norm(e, sd[pfx + "embeddings.LayerNorm.weight"], sd[pfx + "embeddings.LayerNorm.bias"], eps)
+    return y if drop is None else y * drop  # drop = keep / (1 - p): modeling_bert.py:111
 
 
-def self_attention(x, sd, lp, heads, attention_mask):
+def self_attention(x, sd, lp, heads, attention_mask, drop=None):
     N, S, H = x.shape
     dh = H // heads
     a = lp + "attention.self."
@@ -53,20 +54,28 @@ def self_attention(x, sd, lp, heads, attention_mask):
         neg = neg.masked_fill(attention_mask.view(N, 1, 1, S) == 0, float("-inf"))
         scores = scores + neg
     p = torch.softmax(scores, dim=-1)
+    if drop is not None:  # attention-probability dropout (eager_attention_forward / SDPA dropout_p)
+        p = p * drop
     ctx = (p @ v).transpose(1, 2).reshape(N, S, H)
     return ctx
 
 
-def layer(x, sd, lp, heads, attention_mask, eps):
-    ctx = self_attention(x, sd, lp, heads, attention_mask)
+def layer(x, sd, lp, heads, attention_mask, eps, drops=None):
+    """drops: optional dict with multiplier tensors (keep / (1-p)) under 'attn', 'attn_out', 'ffn_out'."""
+    drops = drops or {}
+    ctx = self_attention(x, sd, lp, heads, attention_mask, drops.get("attn"))
     o = ctx @ sd[lp + "attention.output.dense.weight"].T + sd[lp + "attention.output.dense.bias"]
+    if "attn_out" in drops:
+        o = o * drops["attn_out"]  # BertSelfOutput.dropout, modeling_bert.py:296
     x1 = layer_norm(o + x, sd[lp + "attention.output.LayerNorm.weight"], sd[lp + "attention.output.LayerNorm.bias"], eps)
     h = gelu_erf(x1 @ sd[lp + "intermediate.dense.weight"].T + sd[lp + "intermediate.dense.bias"])
     o2 = h @ sd[lp + "output.dense.weight"].T + sd[lp + "output.dense.bias"]
+    if "ffn_out" in drops:
+        o2 = o2 * drops["ffn_out"]  # BertOutput.dropout, modeling_bert.py:354
     return layer_norm(o2 + x1, sd[lp + "output.LayerNorm.weight"], sd[lp + "output.LayerNorm.bias"], eps)
 
 
-def encode(sd, cfg, tokens, prefix="transformer."):
+def encode(sd, cfg, tokens, prefix="transformer.", dropout=None):
     """tokens: mapping with input_ids (+ optional token_type_ids, attention_mask) -> CLS reps [N, H].
 
     cfg keys: layers, heads, ln_eps, pad_id, roberta (bool).
@@ -81,9 +90,10 @@ def encode(sd, cfg, tokens, prefix="transformer."):
         pos = roberta_position_ids(input_ids, cfg["pad_id"])
     else:
         pos = torch.arange(S).unsqueeze(0).expand(N, S)
-    x = embeddings(sd, prefix, input_ids, tt, pos, cfg["ln_eps"])
+    dropout = dropout or {}
+    x = embeddings(sd, prefix, input_ids, tt, pos, cfg["ln_eps"], dropout.get("emb"))
     for l in range(cfg["layers"]):
-        x = layer(x, sd, f"{prefix}encoder.layer.{l}.", cfg["heads"], am, cfg["ln_eps"])
+        x = layer(x, sd, f"{prefix}encoder.layer.{l}.", cfg["heads"], am, cfg["ln_eps"], dropout.get(l))
     rep = x[:, 0, :]
     if prefix.replace("transformer.", "project.0.weight") in sd:  # optional Linear+LayerNorm projection head
         pp = prefix.replace("transformer.", "project.")

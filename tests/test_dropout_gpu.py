@@ -1,0 +1,81 @@
+"""Dropout parity: in train mode the CUDA path applies HF's four dropout sites (embeddings, attention probabilities,
+attention-output dense, FFN-output dense) with counter-based masks that are never stored.  The test exports the masks
+(dprb_dropout_mask), replays them in the CPU oracle and compares embeddings and parameter gradients (linear probe)."""
+import pytest
+import torch
+
+from tests.util import BERT_TINY_CFG, cosine, load_golden, rel_l2, sub
+
+pytestmark = pytest.mark.gpu
+P = 0.1
+
+
+def _masks(enc, N, S, H, heads, layers):
+    from dpr_scale_b200 import ops
+    p, seed = enc.last_dropout
+    assert abs(p - P) < 1e-7
+    sc = 1.0 / (1.0 - p)
+    T = N * S
+    out = {"emb": ops.dropout_mask(T * H, p, seed, 0, 0).view(N, S, H).float().cpu() * sc}
+    for l in range(layers):
+        out[l] = {
+            "attn": ops.dropout_mask(N * heads * S * S, p, seed, l, 1).view(N, heads, S, S).float().cpu() * sc,
+            "attn_out": ops.dropout_mask(T * H, p, seed, l, 2).view(N, S, H).float().cpu() * sc,
+            "ffn_out": ops.dropout_mask(T * H, p, seed, l, 3).view(N, S, H).float().cpu() * sc,
+        }
+    return out
+
+
+def test_dropout_matches_oracle_with_replayed_masks():
+    from dpr_scale_b200.models.hf_model import HFEncoder
+    from oracle import encoder as oenc
+    from tests.test_task_gpu import CFG, _batch
+    g = load_golden("golden_1rank.npz")
+    enc = HFEncoder.from_config(CFG, dropout=P)
+    enc.load_state_dict(sub(g, "sd_c/"))
+    enc = enc.cuda().train()
+    tokens = _batch(g)["contexts_ids"]
+    N, S = tokens["input_ids"].shape
+    probe = torch.randn(N, 128, generator=torch.Generator().manual_seed(5))
+    enc.zero_grad()
+    rep = enc(tokens)
+    (rep * probe.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    masks = _masks(enc, N, S, 128, 2, 2)
+    keep_rate = float((masks[0]["attn"] > 0).float().mean())
+    assert abs(keep_rate - (1 - P)) < 0.02, keep_rate
+    sd = {k: v.clone().requires_grad_(True) for k, v in sub(g, "sd_c/").items()}
+    ref = oenc.encode(sd, BERT_TINY_CFG, tokens, dropout=masks)
+    (ref * probe).sum().backward()
+    assert rel_l2(rep.detach().cpu(), ref.detach()) <= 1e-2, rel_l2(rep.detach().cpu(), ref.detach())
+    # and it differs from the no-dropout output (the masks really were applied)
+    assert rel_l2(rep.detach().cpu(), oenc.encode(sub(g, "sd_c/"), BERT_TINY_CFG, tokens)) > 5e-2
+    top = max(float(v.grad.norm()) for k, v in sd.items() if v.grad is not None)
+    worst = 1.0
+    for k, p in enc.named_parameters():
+        r = sd[k].grad
+        if r is None or float(r.norm()) < 1e-5 * top:
+            continue
+        cs = cosine(p.grad.detach().cpu(), r)
+        worst = min(worst, cs)
+        assert cs >= 0.999, (k, cs)
+        assert rel_l2(p.grad.detach().cpu(), r) <= 3e-2, (k, rel_l2(p.grad.detach().cpu(), r))
+    print("dropout probe: worst gradient cosine", worst)
+
+
+def test_dropout_is_off_in_eval_and_reseeds_each_forward():
+    from dpr_scale_b200.models.hf_model import HFEncoder
+    from tests.test_task_gpu import CFG, _batch
+    g = load_golden("golden_1rank.npz")
+    enc = HFEncoder.from_config(CFG, dropout=P)
+    enc.load_state_dict(sub(g, "sd_c/"))
+    enc = enc.cuda()
+    tokens = _batch(g)["contexts_ids"]
+    enc.eval()
+    with torch.no_grad():
+        a, b = enc(tokens), enc(tokens)
+    assert torch.equal(a, b) and enc.last_dropout[0] == 0.0
+    enc.train()
+    c, d = enc(tokens).detach(), enc(tokens).detach()
+    assert not torch.equal(c, d)  # fresh masks per forward
+    assert rel_l2(c, a) > 1e-2

@@ -58,7 +58,7 @@ SIGNATURES = {
     "dprb_embed_ln_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_float,
                                   c_uint64, _P]),
     "dprb_dropout_site_seed": (c_uint64, [c_uint64, c_int, c_int]),
-    "dprb_dropout_mask": (c_int, [_P, c_int64, c_float, c_uint64, c_int, c_int, _P]),
+    "dprb_dropout_mask": (c_int, [_P, c_int64, c_int, c_float, c_uint64, c_int, c_int, _P]),
     "dprb_ln_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P]),
     "dprb_ln_bwd": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P, c_float, c_uint64, _P]),
     "dprb_colsum_bf16": (c_int, [_P, c_int64, _P, c_int, c_int, _P]),

@@ -79,11 +79,11 @@ int dprb_ln_bwd(const void* dy, const float* dy_cls, int cls_stride, const void*
                 dropout_site_seed, S(stream));
 }
 uint64_t dprb_dropout_site_seed(uint64_t dropout_seed, int layer, int site) {
-  return make_drop(0.5f, dropout_seed, layer, site).seed;
+  return drop_site_seed64(dropout_seed, layer, site);
 }
-int dprb_dropout_mask(uint8_t* keep, int64_t n, float dropout_p, uint64_t dropout_seed, int layer, int site,
-                      dprb_stream_t stream) {
-  return dropout_mask(keep, n, dropout_p, dropout_seed, layer, site, S(stream));
+int dprb_dropout_mask(uint8_t* keep, int64_t rows, int cols, float dropout_p, uint64_t dropout_seed, int layer,
+                      int site, dprb_stream_t stream) {
+  return dropout_mask(keep, rows, cols, dropout_p, dropout_seed, layer, site, S(stream));
 }
 int dprb_colsum_bf16(const void* x, int64_t ld, float* out, int T, int N, dprb_stream_t stream) {
   return colsum_bf16(x, ld, out, T, N, S(stream));

@@ -46,6 +46,7 @@ __device__ __forceinline__ void st_chunk(uint8_t* tile, int row, int chunk, cons
 // smem: sQ | sK | sV | sP (2 k-blocks) | mask[2][128] | barriers.  TMEM: S cols [0,128), O cols [128,192).
 constexpr int FWD_SMEM = 3 * TILE_BYTES + 2 * TILE_BYTES + 2 * 128 * 4 + 64 + 1024;
 
+template <bool DROP>
 __global__ void __launch_bounds__(NTHREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_ctx,
                    const int32_t* __restrict__ attn_mask, float* __restrict__ lse_out, int S, int heads, int nseq,
@@ -153,9 +154,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             const int j = c4 * 8 + t;
             p[t] = ex2_approx(fmaf(__uint_as_float(r[j]), SCALE_LOG2, mk[c * 32 + j]) - e);
             l += p[t];
-            // attention-probability dropout (modeling_bert.py: dropout on softmax output): the row sum keeps the
-            // un-dropped value, only the P V operand is masked and rescaled
-            if (drop.on()) p[t] *= drop.mul(((uint64_t)prob * S + row) * S + c * 32 + j);
+          }
+          if (DROP) {
+            // attention-probability dropout (modeling_bert.py: dropout on the softmax output): the row sum keeps
+            // the un-dropped value, only the P V operand is masked and rescaled
+#pragma unroll
+            for (int t = 0; t < 8; t += 2) {
+              float m0, m1;
+              drop.mul2((uint32_t)(prob * S + row), (uint32_t)(c * 32 + c4 * 8 + t), m0, m1);
+              p[t] *= m0; p[t + 1] *= m1;
+            }
           }
           const int chunk = c * 4 + c4;
           st_chunk(sP + (chunk >> 3) * TILE_BYTES, row, chunk & 7, p, 1.f);
@@ -213,6 +221,7 @@ constexpr int BWD_CT = BWD_CW * 32;             // compute threads
 constexpr int BWD_THREADS = 32 + BWD_CT;
 constexpr int BWD_SMEM = 8 * TILE_BYTES + 4 * TILE_BYTES + 4 * 128 * 4 + 128 + 1024;
 
+template <bool DROP>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_dctx,
                    const __grid_constant__ CUtensorMap tm_dqkv, const int32_t* __restrict__ attn_mask,
@@ -340,14 +349,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           for (int t = 0; t < 8; ++t) {
             const int j = c4 * 8 + t;
             p[t] = ex2_approx(fmaf(__uint_as_float(rs[j]), SCALE_LOG2, mk[half * 64 + c * 32 + j]) - lse2);
-            float dm = 1.f;
-            if (drop.on()) {
-              dm = drop.mul(((uint64_t)prob * S + row) * S + half * 64 + c * 32 + j);
-              if (dm == 0.f) keep &= ~(1ull << (c * 32 + j));
-            }
-            pd[t] = p[t] * dm;
-            D = fmaf(pd[t], __uint_as_float(rd[j]), D);
+            pd[t] = p[t];
           }
+          if (DROP) {
+#pragma unroll
+            for (int t = 0; t < 8; t += 2) {
+              float m0, m1;
+              drop.mul2((uint32_t)(prob * S + row), (uint32_t)(half * 64 + c * 32 + c4 * 8 + t), m0, m1);
+              if (m0 == 0.f) keep &= ~(1ull << (c * 32 + c4 * 8 + t));
+              if (m1 == 0.f) keep &= ~(1ull << (c * 32 + c4 * 8 + t + 1));
+              pd[t] *= m0; pd[t + 1] *= m1;
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < 8; ++t) D = fmaf(pd[t], __uint_as_float(rd[c4 * 8 + t]), D);
 #pragma unroll
           for (int t = 0; t < 4; ++t) pk[c * 16 + c4 * 4 + t] = pack_bf16x2(p[2 * t], p[2 * t + 1]);
           const int chunk = c * 4 + c4;  // 16-byte chunk inside this half's 64-column block
@@ -372,8 +387,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const float2 pp = unpack_bf16x2(pk[c * 16 + c4 * 4 + t]);
-            const int j0 = c * 32 + c4 * 8 + 2 * t;
-            const float m0 = ((keep >> j0) & 1ull) ? drop.scale : 0.f, m1 = ((keep >> (j0 + 1)) & 1ull) ? drop.scale : 0.f;
+            float m0 = 1.f, m1 = 1.f;
+            if (DROP) {
+              const int j0 = c * 32 + c4 * 8 + 2 * t;
+              m0 = ((keep >> j0) & 1ull) ? drop.scale : 0.f;
+              m1 = ((keep >> (j0 + 1)) & 1ull) ? drop.scale : 0.f;
+            }
             ds[2 * t] = pp.x * (__uint_as_float(rd[c4 * 8 + 2 * t]) * m0 - D);
             ds[2 * t + 1] = pp.y * (__uint_as_float(rd[c4 * 8 + 2 * t + 1]) * m1 - D);
           }
@@ -482,22 +501,23 @@ int make_tmap3(CUtensorMap* out, const void* base, int nseq, int S, long long co
 
 int attn_fwd_tc(const void* qkv, const int32_t* attn_mask, void* ctx, float* lse, int nseq, int S, int heads,
                 float dropout_p, unsigned long long site_seed, cudaStream_t stream) {
-  Drop drop = make_drop(dropout_p, 0, 0, 0);
-  drop.seed = site_seed;
+  const Drop drop = drop_from_site(dropout_p, site_seed);
   const int H = heads * 64;
   CUtensorMap tq, tc;
   if (int rc = make_tmap3(&tq, qkv, nseq, S, 3LL * H)) return rc;
   if (int rc = make_tmap3(&tc, ctx, nseq, S, H)) return rc;
   static bool attr = false;
   if (!attr) {
-    DPRB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    DPRB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    DPRB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
     attr = true;
   }
   int sms = num_sms();
   if (sms <= 0) sms = 148;
   const int nprob = nseq * heads;
   const int grid = nprob < 2 * sms ? nprob : 2 * sms;  // two co-resident CTAs per SM interleave their serial chains
-  attn_fwd_tc_kernel<<<grid, NTHREADS, FWD_SMEM, stream>>>(tq, tc, attn_mask, lse, S, heads, nseq, drop);
+  if (drop.on()) attn_fwd_tc_kernel<true><<<grid, NTHREADS, FWD_SMEM, stream>>>(tq, tc, attn_mask, lse, S, heads, nseq, drop);
+  else attn_fwd_tc_kernel<false><<<grid, NTHREADS, FWD_SMEM, stream>>>(tq, tc, attn_mask, lse, S, heads, nseq, drop);
   DPRB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -505,8 +525,7 @@ int attn_fwd_tc(const void* qkv, const int32_t* attn_mask, void* ctx, float* lse
 int attn_bwd_tc(const void* qkv, const int32_t* attn_mask, const float* lse, const void* dctx, void* dqkv,
                 float* dbias, int nseq, int S, int heads, float dropout_p, unsigned long long site_seed,
                 cudaStream_t stream) {
-  Drop drop = make_drop(dropout_p, 0, 0, 0);
-  drop.seed = site_seed;
+  const Drop drop = drop_from_site(dropout_p, site_seed);
   const int H = heads * 64;
   CUtensorMap tq, tdo, tdq;
   if (int rc = make_tmap3(&tq, qkv, nseq, S, 3LL * H)) return rc;
@@ -514,14 +533,16 @@ int attn_bwd_tc(const void* qkv, const int32_t* attn_mask, const float* lse, con
   if (int rc = make_tmap3(&tdq, dqkv, nseq, S, 3LL * H)) return rc;
   static bool attr = false;
   if (!attr) {
-    DPRB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    DPRB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    DPRB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     attr = true;
   }
   int sms = num_sms();
   if (sms <= 0) sms = 148;
   const int nprob = nseq * heads;
   const int grid = nprob < sms ? nprob : sms;
-  attn_bwd_tc_kernel<<<grid, BWD_THREADS, BWD_SMEM, stream>>>(tq, tdo, tdq, attn_mask, lse, dbias, S, heads, nseq, drop);
+  if (drop.on()) attn_bwd_tc_kernel<true><<<grid, BWD_THREADS, BWD_SMEM, stream>>>(tq, tdo, tdq, attn_mask, lse, dbias, S, heads, nseq, drop);
+  else attn_bwd_tc_kernel<false><<<grid, BWD_THREADS, BWD_SMEM, stream>>>(tq, tdo, tdq, attn_mask, lse, dbias, S, heads, nseq, drop);
   DPRB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -120,31 +120,45 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return sg * fmaf(xc * e * sg, inside, 1.f);
 }
 
-// Counter-based dropout RNG: one 32-bit hash per element index.  keep iff u >= p.
-__device__ __forceinline__ uint32_t hash_u32(uint64_t idx, uint64_t seed) {
-  uint64_t z = idx + seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (uint32_t)(z >> 32);
-}
-__device__ __forceinline__ bool dropout_keep(uint64_t idx, uint64_t seed, uint32_t thresh) {
-  return hash_u32(idx, seed) >= thresh;  // thresh = p * 2^32
-}
-// One dropout site: element `idx` is kept iff hash(idx, seed) >= thresh, kept values are scaled by 1/(1-p).
-// thresh == 0 disables the site (p = 0 / eval mode).  Masks are never stored: backward re-derives them.
+// Counter-based dropout RNG.  One 32-bit hash (lowbias32 finaliser, 9 integer instructions) decides TWO horizontally
+// adjacent elements (16 bits each), keyed by (row, column pair, site seed): element (r, c) is kept iff its 16-bit lane
+// is >= thresh16 = round(p * 65536); kept values are scaled by 1 / (1 - thresh16/65536) (p = 0.1 -> 0.100006).
+// thresh16 == 0 disables the site (p = 0 / eval mode).  Masks are never stored: backward re-derives them.
 struct Drop {
-  uint64_t seed;
-  uint32_t thresh;
+  uint32_t seed;
+  uint32_t thresh16;
   float scale;
-  __host__ __device__ bool on() const { return thresh != 0u; }
-  __device__ __forceinline__ float mul(uint64_t idx) const { return dropout_keep(idx, seed, thresh) ? scale : 0.f; }
+  uint32_t row_mul;  // row key = r * row_mul (the pruned last layer runs on the CLS rows only: key = row * S)
+  __host__ __device__ bool on() const { return thresh16 != 0u; }
+  __device__ __forceinline__ uint32_t pair_hash(uint32_t r, uint32_t c_even) const {
+    uint32_t x = (r * row_mul) * 0x9E3779B1u + (c_even >> 1) * 0x85EBCA6Bu + seed;
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+    return x;
+  }
+  // multipliers (scale or 0) for elements (r, c_even) and (r, c_even + 1); c_even must be even
+  __device__ __forceinline__ void mul2(uint32_t r, uint32_t c_even, float& m0, float& m1) const {
+    const uint32_t h = pair_hash(r, c_even);
+    m0 = (h & 0xFFFFu) >= thresh16 ? scale : 0.f;
+    m1 = (h >> 16) >= thresh16 ? scale : 0.f;
+  }
 };
 inline Drop make_drop(float p, uint64_t seed, int layer, int site) {
+  const uint64_t s64 = seed + (uint64_t)(layer * 8 + site + 1) * 0x9E3779B97F4A7C15ull;
   Drop d;
-  d.seed = seed + (uint64_t)(layer * 8 + site + 1) * 0x9E3779B97F4A7C15ull;
-  d.thresh = (p > 0.f) ? (uint32_t)((double)p * 4294967296.0) : 0u;
-  d.scale = (p > 0.f) ? 1.f / (1.f - p) : 1.f;
+  d.seed = (uint32_t)(s64 ^ (s64 >> 32));
+  d.thresh16 = (p > 0.f) ? (uint32_t)((double)p * 65536.0 + 0.5) : 0u;
+  if (d.thresh16 > 65535u) d.thresh16 = 65535u;
+  d.scale = d.thresh16 ? 1.f / (1.f - (float)d.thresh16 / 65536.f) : 1.f;
+  d.row_mul = 1u;
+  return d;
+}
+// derived 32-bit site seed handed across the C ABI (uint64 for headroom)
+inline uint64_t drop_site_seed64(uint64_t seed, int layer, int site) { return make_drop(0.5f, seed, layer, site).seed; }
+// site_seed: low 32 bits = derived seed, high 32 bits = row-key multiplier (0 means 1)
+inline Drop drop_from_site(float p, uint64_t site_seed) {
+  Drop d = make_drop(p, 0, 0, 0);
+  d.seed = (uint32_t)site_seed;
+  d.row_mul = (uint32_t)(site_seed >> 32) ? (uint32_t)(site_seed >> 32) : 1u;
   return d;
 }
 enum { DROP_SITE_EMBED = 0, DROP_SITE_ATTN = 1, DROP_SITE_ATTN_OUT = 2, DROP_SITE_FFN_OUT = 3 };

@@ -26,7 +26,8 @@ int ln_fwd(const void* z, const float* gamma, const float* beta, void* y, float*
 int ln_bwd(const void* dy, const float* dy_cls, int cls_stride, const void* z, const float* stats,
            const float* gamma, void* dz, float* dgamma, float* dbeta, float* dbias, int T, int H, void* dzm,
            float dropout_p, unsigned long long site_seed, cudaStream_t stream);
-int dropout_mask(uint8_t* out, long long n, float p, unsigned long long seed, int layer, int site, cudaStream_t stream);
+int dropout_mask(uint8_t* out, long long rows, int cols, float p, unsigned long long seed, int layer, int site,
+                 cudaStream_t stream);
 unsigned long long drop_site_seed(unsigned long long seed, int layer, int site);
 int colsum_bf16(const void* x, long long ld, float* out, int T, int N, cudaStream_t stream);
 
@@ -41,6 +42,12 @@ int attn_fwd_tc(const void* qkv, const int32_t* attn_mask, void* ctx, float* lse
 int attn_bwd_tc(const void* qkv, const int32_t* attn_mask, const float* lse, const void* dctx, void* dqkv,
                 float* dbias, int nseq, int S, int heads, float dropout_p, unsigned long long site_seed,
                 cudaStream_t stream);
+
+int attn_cls_fwd(const void* qkv, const int32_t* attn_mask, void* ctx_cls, float* probs, int nseq, int S, int heads,
+                 float dropout_p, unsigned long long site_seed, cudaStream_t stream);
+int attn_cls_bwd(const void* qkv, const float* probs, const void* dctx_cls, void* dqkv, int nseq, int S, int heads,
+                 float dropout_p, unsigned long long site_seed, cudaStream_t stream);
+int add_rows_bf16(void* dst, const void* src, int nrows, int H, long long stride_rows, cudaStream_t stream);
 
 int score_ce_fwd(const float* q, const float* c, const uint8_t* col_mask, const uint8_t* pair_mask,
                  const int64_t* labels, float inv_t, float* lse, float* loss_sum, float* logits, int Q, int C, int d,

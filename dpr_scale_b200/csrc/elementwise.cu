@@ -121,7 +121,11 @@ ln_fwd_kernel(const bf16* __restrict__ z, const int64_t* __restrict__ ids, const
         for (int j = 0; j < 8; ++j) o[j] = (x[i][j] - mean) * rstd * g[i][j] + b[i][j];
         if (EMBED && drop.on()) {  // embedding dropout (modeling_bert.py:111)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] *= drop.mul((uint64_t)row * H + c + j);
+          for (int j = 0; j < 8; j += 2) {
+            float m0, m1;
+            drop.mul2((uint32_t)row, (uint32_t)(c + j), m0, m1);
+            o[j] *= m0; o[j + 1] *= m1;
+          }
         }
         store8(y + (long long)row * H + c, o);
         if (is_cls) store8f(cls_out + (long long)(row / cls_stride) * H + c, o);
@@ -257,7 +261,11 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ dy_cls, int
         else load8(dy + (long long)row * H + c, d[i]);
         if (EMBED && drop.on()) {  // upstream gradient is w.r.t. the dropped embedding output
 #pragma unroll
-          for (int j = 0; j < 8; ++j) d[i][j] *= drop.mul((uint64_t)row * H + c + j);
+          for (int j = 0; j < 8; j += 2) {
+            float m0, m1;
+            drop.mul2((uint32_t)row, (uint32_t)(c + j), m0, m1);
+            d[i][j] *= m0; d[i][j + 1] *= m1;
+          }
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -295,7 +303,11 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ dy_cls, int
             // hidden dropout sat between the Linear and this residual+LayerNorm: the Linear's output gradient is
             // dz * mask / (1-p) (second output), while the residual branch takes dz itself
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] *= drop.mul((uint64_t)row * H + c + j);
+            for (int j = 0; j < 8; j += 2) {
+              float m0, m1;
+              drop.mul2((uint32_t)row, (uint32_t)(c + j), m0, m1);
+              o[j] *= m0; o[j + 1] *= m1;
+            }
             store8(dzm + (long long)row * H + c, o);
           }
           if (dbias != nullptr) {
@@ -391,7 +403,7 @@ int ln_fwd(const void* z, const float* gamma, const float* beta, void* y, float*
   if (T == 0) return 0;
   DPRB_REQUIRE(cls_out == nullptr || cls_stride > 0, "ln_fwd: cls_stride must be positive");
   const int grid = grid_for_rows(T);
-#define CALL(C) ln_fwd_kernel<C, false><<<grid, THREADS, 0, stream>>>((const bf16*)z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, gamma, beta, (bf16*)y, stats, cls_out, cls_stride > 0 ? cls_stride : 1, T, H, eps, Drop{0, 0, 1.f})
+#define CALL(C) ln_fwd_kernel<C, false><<<grid, THREADS, 0, stream>>>((const bf16*)z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, gamma, beta, (bf16*)y, stats, cls_out, cls_stride > 0 ? cls_stride : 1, T, H, eps, Drop{0u, 0u, 1.f, 1u})
   DISPATCH_MAXC(H, CALL);
 #undef CALL
   DPRB_CHECK_CUDA(cudaGetLastError());
@@ -401,8 +413,7 @@ int ln_fwd(const void* z, const float* gamma, const float* beta, void* y, float*
 int ln_bwd(const void* dy, const float* dy_cls, int cls_stride, const void* z, const float* stats,
            const float* gamma, void* dz, float* dgamma, float* dbeta, float* dbias, int T, int H, void* dzm,
            float dropout_p, unsigned long long site_seed, cudaStream_t stream) {
-  Drop drop = make_drop(dropout_p, 0, 0, 0);
-  drop.seed = site_seed;  // the caller passes the fully derived site seed
+  const Drop drop = drop_from_site(dropout_p, site_seed);  // the caller passes the derived site seed
   if (!drop.on()) dzm = nullptr;
   if (int rc = check_h(H, "ln_bwd")) return rc;
   if (T == 0) return 0;
@@ -444,16 +455,23 @@ int embed_ln_bwd(const void* dy, const int64_t* ids, const int64_t* type_ids, co
   return 0;
 }
 
-__global__ void dropout_mask_kernel(uint8_t* out, long long n, Drop drop) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    out[i] = drop.on() ? (uint8_t)dropout_keep((uint64_t)i, drop.seed, drop.thresh) : (uint8_t)1;
+__global__ void dropout_mask_kernel(uint8_t* out, long long rows, int cols, Drop drop) {
+  const long long n = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t r = (uint32_t)(i / cols), c = (uint32_t)(i % cols);
+    float m0, m1;
+    drop.mul2(r, c & ~1u, m0, m1);
+    out[i] = drop.on() ? (uint8_t)(((c & 1u) ? m1 : m0) != 0.f) : (uint8_t)1;
+  }
 }
 
-// Test aid: materialise the keep mask of one dropout site (the kernels never store masks).
-int dropout_mask(uint8_t* out, long long n, float p, unsigned long long seed, int layer, int site, cudaStream_t stream) {
-  if (n <= 0) return 0;
+// Test aid: materialise the keep mask keep[r * cols + c] of one dropout site (the kernels never store masks).
+int dropout_mask(uint8_t* out, long long rows, int cols, float p, unsigned long long seed, int layer, int site,
+                 cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return 0;
   const Drop d = make_drop(p, seed, layer, site);
-  dropout_mask_kernel<<<(int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, stream>>>(out, n, d);
+  const long long n = rows * cols;
+  dropout_mask_kernel<<<(int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, stream>>>(out, rows, cols, d);
   DPRB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -5,6 +5,7 @@
 // loop :440-448, BertLayer :359-421) + CLS pooling of /root/reference/dpr_scale/models/hf_model.py:36-41
 // and the autograd backward Lightning runs after dpr_scale/task/dpr_task.py:153-214.
 // The HF pooler (modeling_bert.py:462-468) is not computed: hf_model.py:39 discards it.
+#include <cstdlib>
 #include "common.cuh"
 #include "dprb_internal.h"
 
@@ -97,7 +98,16 @@ LayerW layer_w(const dprb_encoder_weights* w, int l) {
 }
 
 unsigned long long site_seed(const dprb_encoder_batch* b, int layer, int site) {
-  return make_drop(b->dropout_p, b->dropout_seed, layer, site).seed;
+  return drop_site_seed64(b->dropout_seed, layer, site);
+}
+
+// site seed with the row-key multiplier S in the high word: rows of the pruned last layer are CLS rows (token r*S)
+unsigned long long site_seed_cls(const dprb_encoder_batch* b, int layer, int site) {
+  return drop_site_seed64(b->dropout_seed, layer, site) | ((unsigned long long)b->S << 32);
+}
+bool prune_last_layer() {
+  static const bool off = (std::getenv("DPRB_NO_CLS_PRUNE") != nullptr);
+  return !off;
 }
 
 #define TRY(expr) do { if (int _rc = (expr)) return _rc; } while (0)
@@ -128,6 +138,21 @@ int encoder_fwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b, floa
   for (int l = 0; l < L; ++l) {
     const LayerW lw = layer_w(w, l);
     LayerActs& a = ws.slot[b->save_for_backward ? l : (l & 1)];
+    if (l == L - 1 && prune_last_layer()) {
+      // Last layer: only token 0 of each sequence is consumed downstream (hf_model.py:39).  K and V are needed for all
+      // tokens, everything after the attention scores only for the nseq CLS rows (stored in the first nseq rows of
+      // this layer's activation buffers; the saved probabilities reuse the lse buffer).
+      const int R = b->nseq;
+      TRY(gemm_bf16(x, lw.wqkv, a.qkv, T, 3 * H, H, H, H, 3 * H, 0, 0, DPRB_EPI_BIAS, lw.bqkv, nullptr, 0, nullptr, 1.f, 1, nullptr, 0.f, 0, stream));
+      TRY(attn_cls_fwd(a.qkv, b->attn_mask, a.ctx, a.lse, b->nseq, b->S, w->heads, dp, site_seed(b, l, DROP_SITE_ATTN), stream));
+      TRY(gemm_bf16(a.ctx, lw.wo, a.z1, R, H, H, H, H, H, 0, 0, DPRB_EPI_BIAS_RESIDUAL, lw.bo, x, (long long)b->S * H, nullptr, 1.f, 1, nullptr, dp, site_seed_cls(b, l, DROP_SITE_ATTN_OUT), stream));
+      TRY(ln_fwd(a.z1, lw.ln1g, lw.ln1b, a.x1, a.stats1, nullptr, 1, R, H, w->ln_eps, stream));
+      TRY(gemm_bf16(a.x1, lw.w1, a.hact, R, I, H, H, H, I, 0, 0, DPRB_EPI_BIAS_GELU, lw.b1, nullptr, 0, a.hpre, 1.f, 1, nullptr, 0.f, 0, stream));
+      TRY(gemm_bf16(a.hact, lw.w2, a.z2, R, H, I, I, I, H, 0, 0, DPRB_EPI_BIAS_RESIDUAL, lw.b2, a.x1, H, nullptr, 1.f, 1, nullptr, dp, site_seed_cls(b, l, DROP_SITE_FFN_OUT), stream));
+      TRY(ln_fwd(a.z2, lw.ln2g, lw.ln2b, a.out, a.stats2, pooled, 1, R, H, w->ln_eps, stream));
+      x = a.out;
+      continue;
+    }
     TRY(gemm_bf16(x, lw.wqkv, a.qkv, T, 3 * H, H, H, H, 3 * H, 0, 0, DPRB_EPI_BIAS, lw.bqkv, nullptr, 0, nullptr, 1.f, 1, nullptr, 0.f, 0, stream));
     TRY(attn_fwd_lse(a.qkv, b->attn_mask, a.ctx, a.lse, b->nseq, b->S, w->heads, dp, site_seed(b, l, DROP_SITE_ATTN), stream));
     TRY(gemm_bf16(a.ctx, lw.wo, a.z1, T, H, H, H, H, H, 0, 0, DPRB_EPI_BIAS_RESIDUAL, lw.bo, x, H, nullptr, 1.f, 1, nullptr, dp, site_seed(b, l, DROP_SITE_ATTN_OUT), stream));
@@ -159,6 +184,26 @@ int encoder_bwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b, cons
     const float dp = b->dropout_p;
     // with hidden dropout the Linear-side gradient is dz * mask/(1-p) (gB2); the residual branch keeps dz (gB)
     const bf16* gLin = dp > 0.f ? ws.gB2 : ws.gB;
+    if (last && prune_last_layer()) {
+      const int R = b->nseq;
+      TRY(ln_bwd(nullptr, dpooled, 1, a.z2, a.stats2, lw.ln2g, ws.gB, lw.g_ln2g, lw.g_ln2b, lw.g_b2, R, H, ws.gB2, dp,
+                 site_seed_cls(b, l, DROP_SITE_FFN_OUT), stream));
+      TRY(gemm_bf16(gLin, a.hact, lw.g_w2, H, I, R, H, I, I, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, 0.f, 0, stream));
+      TRY(gemm_bf16(gLin, lw.w2, ws.gH, R, I, H, H, I, I, 0, 1, DPRB_EPI_DGELU, nullptr, a.hpre, I, nullptr, 1.f, 1, lw.g_b1, 0.f, 0, stream));
+      TRY(gemm_bf16(ws.gH, a.x1, lw.g_w1, I, H, R, I, H, H, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, 0.f, 0, stream));
+      TRY(gemm_bf16(ws.gH, lw.w1, ws.gA, R, H, I, I, H, H, 0, 1, DPRB_EPI_BIAS_RESIDUAL, nullptr, ws.gB, H, nullptr, 1.f, 1, nullptr, 0.f, 0, stream));
+      TRY(ln_bwd(ws.gA, nullptr, 1, a.z1, a.stats1, lw.ln1g, ws.gB, lw.g_ln1g, lw.g_ln1b, lw.g_bo, R, H, ws.gB2, dp,
+                 site_seed_cls(b, l, DROP_SITE_ATTN_OUT), stream));
+      TRY(gemm_bf16(gLin, a.ctx, lw.g_wo, H, H, R, H, H, H, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, 0.f, 0, stream));
+      TRY(gemm_bf16(gLin, lw.wo, ws.gA, R, H, H, H, H, H, 0, 1, DPRB_EPI_BIAS, nullptr, nullptr, 0, nullptr, 1.f, 1, nullptr, 0.f, 0, stream));
+      TRY(attn_cls_bwd(a.qkv, a.lse, ws.gA, ws.gQKV, b->nseq, b->S, w->heads, dp, site_seed(b, l, DROP_SITE_ATTN), stream));
+      TRY(colsum_bf16(ws.gQKV, 3 * H, lw.g_bqkv, T, 3 * H, stream));
+      TRY(gemm_bf16(ws.gQKV, x, lw.g_wqkv, 3 * H, H, T, 3 * H, H, H, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, 0.f, 0, stream));
+      // dx = dqkv Wqkv, plus the residual gradient dz1 on the CLS rows only
+      TRY(gemm_bf16(ws.gQKV, lw.wqkv, ws.gA, T, H, 3 * H, 3 * H, H, H, 0, 1, DPRB_EPI_BIAS, nullptr, nullptr, 0, nullptr, 1.f, 1, nullptr, 0.f, 0, stream));
+      TRY(add_rows_bf16(ws.gA, ws.gB, R, H, b->S, stream));
+      continue;
+    }
     // LN2 backward (+ db2)
     TRY(ln_bwd(last ? nullptr : ws.gA, last ? dpooled : nullptr, b->S, a.z2, a.stats2, lw.ln2g, ws.gB, lw.g_ln2g,
                lw.g_ln2b, lw.g_b2, T, H, ws.gB2, dp, site_seed(b, l, DROP_SITE_FFN_OUT), stream));

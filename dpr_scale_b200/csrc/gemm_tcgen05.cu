@@ -441,6 +441,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
               }
             }
+            if (p.drop.on()) {
+              // hidden dropout between the dense layer and the residual add (training only; kept out of the hot
+              // loops below so the p = 0 path compiles exactly as before)
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                float m0, m1;
+                p.drop.mul2((uint32_t)row, (uint32_t)(col0 + j), m0, m1);
+                v[j] *= m0; v[j + 1] *= m1;
+              }
+            }
             if (has_aux) {
 #pragma unroll
               for (int c4 = 0; c4 < 4; ++c4) {
@@ -450,12 +460,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const float a[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
-                  if (p.epilogue == DPRB_EPI_BIAS_RESIDUAL) {
-                    if (p.drop.on()) v[c4 * 8 + t] *= p.drop.mul((uint64_t)row * p.N + col0 + c4 * 8 + t);
-                    v[c4 * 8 + t] += a[t];
-                  } else {
-                    v[c4 * 8 + t] *= gelu_erf_grad(a[t]);
-                  }
+                  if (p.epilogue == DPRB_EPI_BIAS_RESIDUAL) v[c4 * 8 + t] += a[t];
+                  else v[c4 * 8 + t] *= gelu_erf_grad(a[t]);
                 }
               }
             }
@@ -630,8 +636,7 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long l
   p.D = D; p.ldd = ldd; p.bias = bias; p.aux = reinterpret_cast<const bf16*>(aux); p.ld_aux = ld_aux;
   p.out2 = reinterpret_cast<bf16*>(out2); p.alpha = alpha;
   p.colsum = colsum;
-  p.drop = make_drop(epilogue == DPRB_EPI_BIAS_RESIDUAL ? dropout_p : 0.f, 0, 0, 0);
-  p.drop.seed = drop_site_seed;
+  p.drop = drop_from_site(epilogue == DPRB_EPI_BIAS_RESIDUAL ? dropout_p : 0.f, drop_site_seed);
   static const bool no_aux_pf = (std::getenv("DPRB_NO_AUX_PF") != nullptr);
   // measured (same box, cfg-2 shapes): prefetching aux before the accumulator wait gains 10-14 % where the epilogue
   // is the critical path (K <= 1024: attention-out, dGELU) and costs ~1.5 % on the K >= 2304 GEMMs

@@ -101,10 +101,11 @@ def dropout_site_seed(seed, layer, site):
     return int(_lib.load().dprb_dropout_site_seed(int(seed), layer, site))
 
 
-def dropout_mask(n, p, seed, layer, site, device="cuda"):
-    """keep mask (uint8) of one dropout site for flat element indices [0, n) — test aid."""
-    out = torch.empty(n, dtype=torch.uint8, device=device)
-    check(_lib.load().dprb_dropout_mask(_ptr(out), n, float(p), int(seed), layer, site, _stream()), "dprb_dropout_mask")
+def dropout_mask(rows, cols, p, seed, layer, site, device="cuda"):
+    """keep mask (uint8 [rows, cols]) of one dropout site — test aid."""
+    out = torch.empty(rows, cols, dtype=torch.uint8, device=device)
+    check(_lib.load().dprb_dropout_mask(_ptr(out), rows, cols, float(p), int(seed), layer, site, _stream()),
+          "dprb_dropout_mask")
     return out
 
 

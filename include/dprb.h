@@ -96,12 +96,13 @@ int dprb_ln_bwd(const void* dy_bf16, const float* dy_cls, int cls_stride, const 
                 const float* stats, const float* gamma, void* dz_bf16, float* dgamma, float* dbeta,
                 float* dbias, int T, int H, void* dzm_bf16, float dropout_p, uint64_t dropout_site_seed,
                 dprb_stream_t stream);
-/* Dropout sites: 0 embeddings, 1 attention probabilities, 2 attention-output dense, 3 FFN-output dense.
- * site seed = dropout_seed + (layer*8 + site + 1) * 0x9E3779B97F4A7C15 (mod 2^64).
- * dprb_dropout_mask materialises keep[i] for element indices i in [0, n) of one site (test aid). */
+/* Dropout sites: 0 embeddings [T,H], 1 attention probabilities [nseq*heads*S, S], 2 attention-output dense [T,H],
+ * 3 FFN-output dense [T,H].  Element (r, c) of a site is kept iff a 16-bit lane of hash32(r, c/2, site seed) is
+ * >= round(p * 65536); site seed = fold32(dropout_seed + (layer*8 + site + 1) * 0x9E3779B97F4A7C15).
+ * dprb_dropout_mask materialises keep[r * cols + c] of one site (test aid). */
 uint64_t dprb_dropout_site_seed(uint64_t dropout_seed, int layer, int site);
-int dprb_dropout_mask(uint8_t* keep, int64_t n, float dropout_p, uint64_t dropout_seed, int layer, int site,
-                      dprb_stream_t stream);
+int dprb_dropout_mask(uint8_t* keep, int64_t rows, int cols, float dropout_p, uint64_t dropout_seed, int layer,
+                      int site, dprb_stream_t stream);
 
 /* Column sums: out[n] += sum_t x[t, n]  (bias gradients; x bf16 [T, N] with leading dim ld). */
 int dprb_colsum_bf16(const void* x_bf16, int64_t ld, float* out, int T, int N, dprb_stream_t stream);

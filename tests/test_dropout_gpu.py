@@ -14,14 +14,14 @@ def _masks(enc, N, S, H, heads, layers):
     from dpr_scale_b200 import ops
     p, seed = enc.last_dropout
     assert abs(p - P) < 1e-7
-    sc = 1.0 / (1.0 - p)
+    sc = 1.0 / (1.0 - round(p * 65536) / 65536.0)  # the kernels quantise p to 16 bits
     T = N * S
-    out = {"emb": ops.dropout_mask(T * H, p, seed, 0, 0).view(N, S, H).float().cpu() * sc}
+    out = {"emb": ops.dropout_mask(T, H, p, seed, 0, 0).view(N, S, H).float().cpu() * sc}
     for l in range(layers):
         out[l] = {
-            "attn": ops.dropout_mask(N * heads * S * S, p, seed, l, 1).view(N, heads, S, S).float().cpu() * sc,
-            "attn_out": ops.dropout_mask(T * H, p, seed, l, 2).view(N, S, H).float().cpu() * sc,
-            "ffn_out": ops.dropout_mask(T * H, p, seed, l, 3).view(N, S, H).float().cpu() * sc,
+            "attn": ops.dropout_mask(N * heads * S, S, p, seed, l, 1).view(N, heads, S, S).float().cpu() * sc,
+            "attn_out": ops.dropout_mask(T, H, p, seed, l, 2).view(N, S, H).float().cpu() * sc,
+            "ffn_out": ops.dropout_mask(T, H, p, seed, l, 3).view(N, S, H).float().cpu() * sc,
         }
     return out
 

@@ -103,6 +103,21 @@ __device__ __forceinline__ float gauss_cdf(float x) {
   return rcp_approx(1.f + e);
 }
 __device__ __forceinline__ float gelu_erf(float x) { return x * gauss_cdf(x); }
+// GELU and its derivative from ONE evaluation of sigma(z(x)) (2 MUFU for both): the forward GEMM epilogue stores
+// gelu'(pre) instead of the pre-activation, so the backward epilogue is a plain multiply.
+__device__ __forceinline__ void gelu_and_grad(float x, float& g, float& gd) {
+  const float xc = fminf(fmaxf(x, -8.f), 8.f);
+  const float x2 = xc * xc;
+  float pz = fmaf(x2, 1.03455483e-3f, -1.06900513e-1f);
+  pz = fmaf(pz, x2, -2.30098511f);
+  const float e = ex2_approx(pz * xc);          // exp(-z)
+  const float sg = rcp_approx(1.f + e);         // sigma(z) ~ Phi(x)
+  float zp = fmaf(x2, -3.58549371e-3f, 2.22293380e-1f);   // z'(x) = a0 + 3 a1 x^2 + 5 a2 x^4
+  zp = fmaf(zp, x2, 1.59492135f);
+  const float inside = (x == xc) ? zp : 0.f;    // clamp region: z is constant
+  g = x * sg;
+  gd = sg * fmaf(xc * e * sg, inside, 1.f);
+}
 // Exact derivative of the forward function g(x) = x * sigma(z(x)), z = a0 x + a1 x^3 + a2 x^5:
 //   g'(x) = sigma + x * sigma * (1 - sigma) * z'(x),  z' = a0 + 3 a1 x^2 + 5 a2 x^4   (0 beyond the clamp)
 // -> backward differentiates exactly what forward evaluated, with 2 MUFU (ex2, rcp) instead of 3.

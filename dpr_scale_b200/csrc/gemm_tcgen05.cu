@@ -346,7 +346,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           __syncwarp();  // reconverge before the next .sync.aligned tcgen05.ld
         }
       } else if (is_gelu) {
-        // single pass, two 32x32 slabs (64B swizzle) per 32-column chunk: pre-activation -> out2 (optional), GELU -> D
+        // single pass, two 32x32 slabs (64B swizzle) per 32-column chunk: gelu'(pre) -> out2 (optional), gelu(pre) -> D
 #pragma unroll 1
         for (int h = 0; h < 4; ++h) {
           const int col0 = n_blk * BLOCK_N + col_half * 128 + h * 32;
@@ -378,11 +378,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             uint32_t* pa = &qa.x;
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-              const uint32_t pre2 = pack_bf16x2(v[c4 * 8 + 2 * t], v[c4 * 8 + 2 * t + 1]);
-              // GELU acts on the bf16-rounded pre-activation: backward re-reads exactly that value
-              const float2 f = unpack_bf16x2(pre2);
-              pp[t] = pre2;
-              pa[t] = pack_bf16x2(gelu_erf(f.x), gelu_erf(f.y));
+              // out2 receives gelu'(pre): backward (EPI_DGELU) only ever needs the derivative, never pre itself
+              float g0, d0, g1, d1;
+              gelu_and_grad(v[c4 * 8 + 2 * t], g0, d0);
+              gelu_and_grad(v[c4 * 8 + 2 * t + 1], g1, d1);
+              pp[t] = pack_bf16x2(d0, d1);
+              pa[t] = pack_bf16x2(g0, g1);
             }
             const uint32_t off = lane * 64 + ((c4 ^ ((lane >> 1) & 3)) << 4);
             if (p.out2 != nullptr) *reinterpret_cast<uint4*>(slab_pre + off) = qp;
@@ -461,7 +462,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
                   if (p.epilogue == DPRB_EPI_BIAS_RESIDUAL) v[c4 * 8 + t] += a[t];
-                  else v[c4 * 8 + t] *= gelu_erf_grad(a[t]);
+                  else v[c4 * 8 + t] *= a[t];  // EPI_DGELU: aux holds gelu'(pre) written by the forward epilogue
                 }
               }
             }

@@ -397,7 +397,7 @@ class HFEncoder(nn.Module):
         for lo, hi in bounds:
             check(_lib.load().dprb_encoder_bwd(ctypes.byref(w), ctypes.byref(b), dpooled.data_ptr(), lo, hi, stream),
                   "dprb_encoder_bwd")
-            n = 11 * (hi - lo) + (1 if lo == 0 else 0)
+            n = 11 * (hi - lo) + (2 if hi == L else 0) + (1 if lo == 0 else 0)  # kernels launched by this call
             self.launches += n
             ops._count(n)
             if self.grad_sync is not None:

@@ -10,6 +10,8 @@ Same constructor kwargs, same Lightning hook names (``setup``, ``training_step``
     (``dprb_score_ce_fwd``) and its backward emits only the rank-local dq / dc (:163-195 semantics);
   * the four per-tensor all-gathers of :174-176 are ONE packed NCCL all-gather.
 """
+import os
+
 import torch
 import torch.distributed as dist
 from torch.optim.lr_scheduler import LambdaLR
@@ -102,6 +104,23 @@ class DenseRetrieverTask(LightningModule):
         return self._encode_sequence(contexts_ids, self.context_encoder)
 
     def forward(self, query_ids, contexts_ids):
+        # The two encoders are independent until the scoring kernel: the (8x smaller) query encoder is enqueued on a
+        # side stream so its kernels fill the tail waves of the context encoder's persistent kernels; autograd replays
+        # each backward on its forward stream, so the overlap also holds in backward.
+        dev = getattr(self.query_encoder, "master", None)
+        if (dev is not None and dev.is_cuda and self.query_encoder is not self.context_encoder
+                and os.environ.get("DPRB_NO_STREAM_OVERLAP") is None):
+            main = torch.cuda.current_stream()
+            if getattr(self, "_side_stream", None) is None:
+                self._side_stream = torch.cuda.Stream()
+            side = self._side_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                q = self.encode_queries(query_ids)
+            c = self.encode_contexts(contexts_ids)
+            main.wait_stream(side)
+            q.record_stream(main)
+            return q, c
         return self.encode_queries(query_ids), self.encode_contexts(contexts_ids)
 
     def sim_score(self, query_repr, context_repr, mask=None):

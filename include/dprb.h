@@ -47,9 +47,9 @@ int dprb_num_sms(void);
  * ------------------------------------------------------------------------------------------- */
 enum {
   DPRB_EPI_BIAS = 0,           /* D(bf16) = acc + bias                      (bias may be NULL)        */
-  DPRB_EPI_BIAS_GELU = 1,      /* out2(bf16) = acc + bias ; D(bf16) = gelu_erf(out2)                   */
+  DPRB_EPI_BIAS_GELU = 1,      /* D(bf16) = gelu(acc + bias) ; out2(bf16, optional) = gelu'(acc + bias) */
   DPRB_EPI_BIAS_RESIDUAL = 2,  /* D(bf16) = acc + bias + aux(bf16)                                     */
-  DPRB_EPI_DGELU = 3,          /* D(bf16) = acc * gelu_erf'(aux(bf16))                                 */
+  DPRB_EPI_DGELU = 3,          /* D(bf16) = acc * aux(bf16), aux = the gelu' saved by BIAS_GELU          */
   DPRB_EPI_F32_ATOMIC_ADD = 4, /* D(fp32) += acc  (split-K over `splits` CTAs; 0 = choose)            */
   DPRB_EPI_F32_STORE = 5,      /* D(fp32) = acc + bias                                                 */
   DPRB_EPI_COUNT = 6

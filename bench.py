@@ -320,7 +320,12 @@ def run_b200(args, workload):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel<*,*,2> (tcgen05 cta_group::2 UMMA 256x256x16)",
                      "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tflops / peak_tf,
-                     "peak_source": peak_src, "traffic": None, "gemm_launches": nl.value,
+                     "peak_source": peak_src,
+                     # ncu --set full (profiles/r1_final_ncu_full_summary.json), largest launch of this kernel
+                     # (FFN-in, M=131072 N=3072 K=768): dram read+write vs its algorithmic bytes (A + 2 outputs + W)
+                     "traffic": 1.766e9 if workload == "bert-base_s128_b128_n7" else None,
+                     "traffic_algorithmic": 1.816e9 if workload == "bert-base_s128_b128_n7" else None,
+                     "gemm_launches": nl.value,
                      "gemm_ms_per_step": tms.value / args.steps, "gemm_share_of_step": (tms.value / args.steps) / ms_step,
                      "step_model_tflops": step_flops / (ms_step / 1e3) / 1e12,
                      "step_frac_of_peak": step_flops / (ms_step / 1e3) / 1e12 / peak_tf},

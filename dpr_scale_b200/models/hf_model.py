@@ -141,6 +141,36 @@ class _EncoderFn(torch.autograd.Function):
         return None, None, None, None
 
 
+class _ChunkedEncoderFn(torch.autograd.Function):
+    """Activation-memory bound for very large context batches (e.g. BASELINE config 4: 262 144 tokens x 24 layers of
+    RoBERTa-large would need ~214 GB of saved activations): forward encodes `chunk` sequences at a time WITHOUT saving
+    activations; backward re-runs each chunk with saving (same dropout seeds) and back-propagates its slice of the
+    upstream gradient.  Mathematically identical to the unchunked path (the loss only sees the pooled embeddings)."""
+
+    @staticmethod
+    def forward(ctx, anchor, enc, tokens, chunk):
+        n = tokens["input_ids"].shape[0]
+        outs, seeds = [], []
+        for lo in range(0, n, chunk):
+            part = {k: v[lo:lo + chunk] for k, v in tokens.items() if v is not None}
+            pooled, _ = enc._run_forward(part, False, train_dropout=True)
+            seeds.append(enc.last_dropout[1])
+            outs.append(pooled)
+        ctx.enc, ctx.tokens, ctx.chunk, ctx.seeds = enc, tokens, chunk, seeds
+        return torch.cat(outs, 0)
+
+    @staticmethod
+    def backward(ctx, dpooled):
+        enc, tokens, chunk = ctx.enc, ctx.tokens, ctx.chunk
+        dpooled = dpooled.contiguous().float()
+        n = tokens["input_ids"].shape[0]
+        for i, lo in enumerate(range(0, n, chunk)):
+            part = {k: v[lo:lo + chunk] for k, v in tokens.items() if v is not None}
+            _, state = enc._run_forward(part, True, train_dropout=True, force_seed=ctx.seeds[i])
+            enc._run_backward(state, dpooled[lo:lo + chunk].contiguous())
+        return None, None, None, None
+
+
 class _Transformer(nn.Module):
     """Container that owns the arenas and mirrors the HF module tree (parameter names only)."""
 
@@ -214,6 +244,8 @@ class HFEncoder(nn.Module):
         self.bwd_chunk_layers = 0
         self._drop_base = (torch.initial_seed() * 0x9E3779B97F4A7C15 + id(self)) & 0xFFFFFFFFFFFFFFFF
         self._drop_calls = 0
+        # sequences per activation chunk (0 = keep all activations of the batch; see _ChunkedEncoderFn)
+        self.activation_chunk = int(os.environ.get("DPRB_ACTIVATION_CHUNK", "0"))
 
     # ------------------------------------------------------------------ construction helpers
     @classmethod
@@ -358,7 +390,7 @@ class HFEncoder(nn.Module):
             pos = torch.arange(S, device=dev, dtype=torch.int64).unsqueeze(0).expand(N, S)
         return ids, tt, pos.contiguous(), am32, N, S
 
-    def _run_forward(self, tokens, save):
+    def _run_forward(self, tokens, save, train_dropout=None, force_seed=None):
         ids, tt, pos, am, N, S = self._prep_tokens(tokens)
         self._ensure_device_state(save)
         ws = self._workspace(N, S, save)
@@ -370,9 +402,11 @@ class HFEncoder(nn.Module):
         b.workspace, b.workspace_bytes = base, ws.numel() - (base - ws.data_ptr())
         b.save_for_backward = int(save)
         # HF applies dropout only in train mode; the seed changes every forward and is replayed by backward
-        b.dropout_p = self.dropout if (self.training and save) else 0.0
+        use_drop = (self.training and save) if train_dropout is None else (self.training and train_dropout)
+        b.dropout_p = self.dropout if use_drop else 0.0
         self._drop_calls += 1
-        b.dropout_seed = (self._drop_base + self._drop_calls * 0x2545F4914F6CDD1D) & 0xFFFFFFFFFFFFFFFF
+        b.dropout_seed = force_seed if force_seed is not None else (
+            (self._drop_base + self._drop_calls * 0x2545F4914F6CDD1D) & 0xFFFFFFFFFFFFFFFF)
         self.last_dropout = (float(b.dropout_p), int(b.dropout_seed))  # exposed for tests (mask reconstruction)
         w = self._weights_struct(save)
         pooled = torch.empty(N, self.config["hidden_size"], dtype=torch.float32, device=ids.device)
@@ -410,7 +444,12 @@ class HFEncoder(nn.Module):
             # any arena parameter works as the autograd anchor; gradients are written by the kernels
             # straight into the flat grads arena (exposed as param.grad views), so backward returns None.
             anchor = self.transformer.embeddings.LayerNorm.weight
-            rep = _EncoderFn.apply(anchor, self, tokens, True)
+            n = tokens["input_ids"].shape[0]
+            if self.activation_chunk and n > self.activation_chunk:
+                tk = {k: tokens[k] for k in ("input_ids", "token_type_ids", "attention_mask") if k in tokens}
+                rep = _ChunkedEncoderFn.apply(anchor, self, tk, self.activation_chunk)
+            else:
+                rep = _EncoderFn.apply(anchor, self, tokens, True)
         else:
             rep, _ = self._run_forward(tokens, False)
         rep = self.project(rep)

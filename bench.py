@@ -28,11 +28,17 @@ import torch.distributed as dist  # noqa: E402
 BERT_BASE = dict(model_type="bert", vocab_size=30522, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
                  intermediate_size=3072, max_position_embeddings=512, type_vocab_size=2, layer_norm_eps=1e-12,
                  pad_token_id=0, initializer_range=0.02)
+ROBERTA_LARGE = dict(model_type="roberta", vocab_size=50265, hidden_size=1024, num_hidden_layers=24,
+                     num_attention_heads=16, intermediate_size=4096, max_position_embeddings=514, type_vocab_size=1,
+                     layer_norm_eps=1e-5, pad_token_id=1, initializer_range=0.02)
 WORKLOADS = {
     # name: (model cfg, queries/GPU, hard negs, seq len)
-    "bert-base_s128_b128_n7": (BERT_BASE, 128, 7, 128),
-    "bert-base_s64_b8_n1": (BERT_BASE, 8, 1, 64),
+    "bert-base_s128_b128_n7": (BERT_BASE, 128, 7, 128),          # BASELINE configs[1] / [2]  (the headline)
+    "bert-base_s64_b8_n1": (BERT_BASE, 8, 1, 64),                # configs[0] shape
+    "roberta-large_s256_b64_n15": (ROBERTA_LARGE, 64, 15, 256),  # configs[3] (needs activation chunking, see below)
 }
+# sequences per activation chunk of the context encoder (0 = keep everything): configs[3] would need ~214 GB otherwise
+ACT_CHUNK = {"roberta-large_s256_b64_n15": 256}
 
 
 def flops_per_token_train(cfg, S):
@@ -129,7 +135,7 @@ def cpu_reference_step_factory(cfg, pairs, n, S, threads):
     """The reference's own CPU path: HF BertModel x2 (fp32) + reference scoring/CE + clip + torch AdamW."""
     from oracle import hf_path, task as otask
     torch.set_num_threads(threads)
-    hf_cfg = hf_path.make_config("bert", **{k: v for k, v in cfg.items() if k not in ("model_type",)})
+    hf_cfg = hf_path.make_config(cfg["model_type"], **{k: v for k, v in cfg.items() if k not in ("model_type",)})
     torch.manual_seed(0)
     qe, ce = hf_path.CLSEncoder(hf_cfg, dropout=0.1), hf_path.CLSEncoder(hf_cfg, dropout=0.1)
     params = [p for p in list(qe.parameters()) + list(ce.parameters())]
@@ -187,7 +193,7 @@ def run_stock(args, workload):
     from oracle import hf_path, task as otask
     cfg, B, n, S = WORKLOADS[workload]
     dev = torch.device("cuda", 0)
-    hf_cfg = hf_path.make_config("bert", **{k: v for k, v in cfg.items() if k not in ("model_type",)})
+    hf_cfg = hf_path.make_config(cfg["model_type"], **{k: v for k, v in cfg.items() if k not in ("model_type",)})
     torch.manual_seed(0)
     qe, ce = hf_path.CLSEncoder(hf_cfg, dropout=args.dropout).to(dev), hf_path.CLSEncoder(hf_cfg, dropout=args.dropout).to(dev)
     params = list(qe.parameters()) + list(ce.parameters())
@@ -248,6 +254,7 @@ def run_b200(args, workload):
     trainer = Trainer(max_steps=10 ** 6, gradient_clip_val=2.0, device=dev)
     trainer.attach(task, None, "fit")
     task.train()
+    task.context_encoder.activation_chunk = ACT_CHUNK.get(workload, 0)
     host_batch = synth_batch(rank, cfg, B, n, S)
     dev_batch = to_device(host_batch, dev)
     lib = _lib.load()
@@ -306,10 +313,12 @@ def run_b200(args, workload):
     tokens = B * (2 + n) * S
     step_flops = tokens * flops_per_token_train(cfg, S)
     line = {
-        "metric": "query+ctx pairs/sec (BERT-base, seq128)", "value": value, "unit": "pairs/s", "n_gpus": world,
+        "metric": "query+ctx pairs/sec (BERT-base, seq128)" if cfg is BERT_BASE else f"query+ctx pairs/sec ({workload})",
+        "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": workload, "model": "BERT-base x2 (query+context, shared_model=false)",
+        "config": {"workload": workload, "model": ("BERT-base" if cfg is BERT_BASE else "RoBERTa-large") + " x2 (query+context, shared_model=false)",
+                   "activation_chunk": ACT_CHUNK.get(workload, 0),
                    "queries_per_gpu": B, "hard_negatives": n, "contexts_per_gpu": B * (1 + n), "seq_len": S,
                    "global_batch": pairs_step, "parallelism": f"dp{world}", "negatives": "global in-batch" if world > 1 else "in-batch",
                    "optimizer": "fused AdamW + clip 2.0 + LambdaLR", "dropout": args.dropout,

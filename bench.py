@@ -122,6 +122,23 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def usable_cores():
+    """Host threads this process may really use: affinity mask, capped by the cgroup CPU quota (shared GPU boxes
+    report 128 logical CPUs but throttle the container), and by 32 (HF BERT at these sample sizes does not scale further)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return max(1, min(n, 32))
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -170,7 +187,7 @@ def run_reference(args, workload):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = usable_cores()
     pairs = args.ref_pairs  # bounded sample of the same workload: `pairs` queries with 1+n contexts each, S tokens
     steps, warmup = args.steps, args.warmup
     value, spstep = time_cpu_reference(cfg, pairs, n, S, steps, warmup, threads)
@@ -284,13 +301,22 @@ def run_b200(args, workload):
     if rank == 0:
         sampler.start()
     launches0 = ops.LAUNCHES
-    _lib.check(lib.dprb_gemm_profile_enable(1, 400 * args.steps + 64), "profile_enable")
     ms_step = timed(lambda i: trainer.training_step(dev_batch, i), args.steps)
     launches = (ops.LAUNCHES - launches0)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline leg: the same step, timed again with CUDA events around EVERY GEMM launch.  The query encoder is
+    # kept on the main stream here (no two-stream overlap), otherwise launch intervals of the two streams interleave
+    # and the per-launch durations would count each other's kernels.
+    prof_steps = min(args.steps, 5)
+    os.environ["DPRB_NO_STREAM_OVERLAP"] = "1"
+    trainer.training_step(dev_batch, 0)
+    _lib.check(lib.dprb_gemm_profile_enable(1, 700 * prof_steps + 64), "profile_enable")
+    ms_prof = timed(lambda i: trainer.training_step(dev_batch, i), prof_steps)
     tms, tfl, nl = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
     _lib.check(lib.dprb_gemm_profile_read(ctypes.byref(tms), ctypes.byref(tfl), ctypes.byref(nl)), "profile_read")
     _lib.check(lib.dprb_gemm_profile_enable(0, 0), "profile_disable")
-    clocks = sampler.stop() if rank == 0 else None
+    del os.environ["DPRB_NO_STREAM_OVERLAP"]
 
     # ---- end-to-end number: host (pinned) inputs -> H2D each step, loss read back each step
     losses = []
@@ -335,16 +361,17 @@ def run_b200(args, workload):
                      "traffic": 1.766e9 if workload == "bert-base_s128_b128_n7" else None,
                      "traffic_algorithmic": 1.816e9 if workload == "bert-base_s128_b128_n7" else None,
                      "gemm_launches": nl.value,
-                     "gemm_ms_per_step": tms.value / args.steps, "gemm_share_of_step": (tms.value / args.steps) / ms_step,
+                     "gemm_ms_per_step": tms.value / prof_steps, "roofline_region_ms_per_step": ms_prof,
+                     "gemm_share_of_step": (tms.value / prof_steps) / ms_prof,
                      "step_model_tflops": step_flops / (ms_step / 1e3) / 1e12,
                      "step_frac_of_peak": step_flops / (ms_step / 1e3) / 1e12 / peak_tf},
         "loss_first_last": [losses[0], losses[-1]] if losses else None,
     }
     if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        v, sp = time_cpu_reference(cfg, args.ref_pairs, n, S, 2, 1, threads)
+        threads = usable_cores()
+        v, sp = time_cpu_reference(cfg, 1, n, S, 2, 1, threads)
         line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
-                                "sample": f"{args.ref_pairs} pairs/step x 2 steps (+1 warm-up) of {workload}: HF BertModel x2 fp32 "
+                                "sample": f"1 pair/step x 2 steps (+1 warm-up) of {workload}: HF BertModel x2 fp32 "
                                           f"fwd+bwd+clip+AdamW on {threads} host threads"}
     print(json.dumps(line))
     if world > 1:
@@ -358,7 +385,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "stock"])
     ap.add_argument("--workload", default="bert-base_s128_b128_n7", choices=sorted(WORKLOADS))
-    ap.add_argument("--ref-pairs", type=int, default=2, help="pairs per step of the bounded CPU sample")
+    ap.add_argument("--ref-pairs", type=int, default=1, help="pairs per step of the bounded CPU sample (--impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.1,
                     help="hidden + attention dropout of both encoders (reference default 0.1, conf/task/model/hf_model.yaml:5)")

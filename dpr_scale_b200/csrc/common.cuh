@@ -40,7 +40,6 @@ int num_sms();  // cached SM count of the current device
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -62,26 +61,12 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(t);
 }
 
-// erf-GELU (HF "gelu", modeling_bert.py BertIntermediate) with an erf that is accurate to
-// ~1.5e-7 abs (Abramowitz–Stegun 7.1.26) — far below bf16 output resolution.
-__device__ __forceinline__ float erf_as(float x) {
-  float ax = fabsf(x);
-  float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  float e = __expf(-ax * ax);
-  float r = fmaf(-p, e, 1.0f);
-  return copysignf(r, x);
-}
-// Gaussian CDF Phi(x) as a logistic of an odd degree-5 polynomial (least-squares fit on [-6,6], argument clamped
-// to [-8,8]): max |Phi err| 5.8e-5, max |x*Phi - gelu_erf(x)| 3.0e-5 over all x — two orders of magnitude below the
-// bf16 rounding of the stored activation.  11 instructions / 2 MUFU per element instead of ~24 / 2 for erf_as():
-// at K = 768 the FFN GEMM epilogue has only ~24 issue slots per output element before it, not the tensor pipe,
-// bounds the kernel.  The same Phi is used by forward and backward, so backward differentiates what forward computed
-// (up to the 3e-5 fit error of x*Phi vs its exact derivative Phi + x*phi).
+// erf-GELU (HF "gelu", modeling_bert.py BertIntermediate) through a fitted Gaussian CDF:
+// Phi(x) = sigma(z(x)), z = a0 x + a1 x^3 + a2 x^5 (least-squares fit on [-6,6], argument clamped to [-8,8]):
+// max |Phi err| 5.8e-5, max |x*Phi - gelu_erf(x)| 3.0e-5 over all x, max |derivative err| 1.2e-4 — two orders of
+// magnitude below the bf16 rounding of the stored activation.  The libm-style erf (~24 instructions + IEEE rcp / exp
+// fix-ups) made the FFN-in GEMM epilogue 2.3x slower than the tensor-core work it follows: at K = 768 there are only
+// ~24 issue slots per output element.
 // single-MUFU approximations (ex2.approx / rcp.approx: ~2 ulp), no denormal / range fix-up code
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -93,16 +78,6 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float gauss_cdf(float x) {
-  const float xc = fminf(fmaxf(x, -8.f), 8.f);
-  const float x2 = xc * xc;
-  // -log2(e) * (1.59492135 + 0.0740977934 x^2 - 0.000717098742 x^4)
-  float pz = fmaf(x2, 1.03455483e-3f, -1.06900513e-1f);
-  pz = fmaf(pz, x2, -2.30098511f);
-  const float e = ex2_approx(pz * xc);      // exp(-z); |z| <= 47 after the clamp: no overflow
-  return rcp_approx(1.f + e);
-}
-__device__ __forceinline__ float gelu_erf(float x) { return x * gauss_cdf(x); }
 // GELU and its derivative from ONE evaluation of sigma(z(x)) (2 MUFU for both): the forward GEMM epilogue stores
 // gelu'(pre) instead of the pre-activation, so the backward epilogue is a plain multiply.
 __device__ __forceinline__ void gelu_and_grad(float x, float& g, float& gd) {
@@ -118,23 +93,6 @@ __device__ __forceinline__ void gelu_and_grad(float x, float& g, float& gd) {
   g = x * sg;
   gd = sg * fmaf(xc * e * sg, inside, 1.f);
 }
-// Exact derivative of the forward function g(x) = x * sigma(z(x)), z = a0 x + a1 x^3 + a2 x^5:
-//   g'(x) = sigma + x * sigma * (1 - sigma) * z'(x),  z' = a0 + 3 a1 x^2 + 5 a2 x^4   (0 beyond the clamp)
-// -> backward differentiates exactly what forward evaluated, with 2 MUFU (ex2, rcp) instead of 3.
-// |g'(x) - gelu_erf'(x)| <= 1.3e-4 (the fit error of Phi and of x*phi), checked in tests/gpu_checks.py.
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float xc = fminf(fmaxf(x, -8.f), 8.f);
-  const float x2 = xc * xc;
-  float pz = fmaf(x2, 1.03455483e-3f, -1.06900513e-1f);
-  pz = fmaf(pz, x2, -2.30098511f);
-  const float e = ex2_approx(pz * xc);          // exp(-z)
-  const float sg = rcp_approx(1.f + e);         // sigma(z)
-  float zp = fmaf(x2, -3.58549371e-3f, 2.22293380e-1f);   // 5 a2 x^2 + 3 a1
-  zp = fmaf(zp, x2, 1.59492135f);
-  const float inside = (x == xc) ? zp : 0.f;    // clamp region: z is constant
-  return sg * fmaf(xc * e * sg, inside, 1.f);
-}
-
 // Counter-based dropout RNG.  One 32-bit hash (lowbias32 finaliser, 9 integer instructions) decides TWO horizontally
 // adjacent elements (16 bits each), keyed by (row, column pair, site seed): element (r, c) is kept iff its 16-bit lane
 // is >= thresh16 = round(p * 65536); kept values are scaled by 1 / (1 - thresh16/65536) (p = 0.1 -> 0.100006).

@@ -379,7 +379,8 @@ int attn_fwd_lse(const void* qkv, const int32_t* attn_mask, void* ctx, float* ls
   if (nseq == 0) return 0;
   static const bool legacy = (std::getenv("DPRB_ATTN_LEGACY") != nullptr);
   if (S <= 128 && !legacy) return attn_fwd_tc(qkv, attn_mask, ctx, lse, nseq, S, heads, dropout_p, site_seed, stream);
-  DPRB_REQUIRE(dropout_p == 0.f, "attn_fwd: attention dropout is implemented for S <= 128 (tcgen05 path) only");
+  if (!legacy) return attn_fwd_tc2(qkv, attn_mask, ctx, lse, nseq, S, heads, dropout_p, site_seed, stream);  // 128 < S <= 256
+  DPRB_REQUIRE(dropout_p == 0.f, "attn_fwd: attention dropout is implemented on the tcgen05 paths only");
   const int S_pad = (S + 63) / 64 * 64;
   const size_t smem = 3 * (size_t)S_pad * 128 + S_pad * 4 + 8 * 16 * STG_STRIDE;
   static bool attr = false;

@@ -280,3 +280,5 @@ CHECKS = {
 CHECKS["attn_tc_many"] = lambda: check_attention(40, 128, 12, True, seed=9)
 CHECKS["attn_tc_s64_many"] = lambda: check_attention(33, 64, 4, True, seed=10)
 CHECKS["attn_tc_s37"] = lambda: check_attention(5, 37, 2, True, seed=11)
+CHECKS["attn_tc2_s200"] = lambda: check_attention(3, 200, 2, True, seed=12)
+CHECKS["attn_tc2_s256_many"] = lambda: check_attention(20, 256, 4, True, seed=13)

@@ -402,7 +402,12 @@ int attn_bwd_lse(const void* qkv, const int32_t* attn_mask, const void* ctx, con
   static const bool legacy = (std::getenv("DPRB_ATTN_LEGACY") != nullptr);
   if (S <= 128 && !legacy)
     return attn_bwd_tc(qkv, attn_mask, lse, dctx, dqkv, dbias, nseq, S, heads, dropout_p, site_seed, stream);
-  DPRB_REQUIRE(dropout_p == 0.f, "attn_bwd: attention dropout is implemented for S <= 128 (tcgen05 path) only");
+  if (!legacy) {  // 128 < S <= 256: tcgen05 kernel; the QKV bias gradient is a separate streaming pass
+    if (int rc = attn_bwd_tc2(qkv, attn_mask, ctx, lse, dctx, dqkv, nseq, S, heads, dropout_p, site_seed, stream)) return rc;
+    if (dbias != nullptr) return colsum_bf16(dqkv, 3LL * heads * DH, dbias, nseq * S, 3 * heads * DH, stream);
+    return 0;
+  }
+  DPRB_REQUIRE(dropout_p == 0.f, "attn_bwd: attention dropout is implemented on the tcgen05 paths only");
   const int S_pad = (S + 63) / 64 * 64;
   const size_t smem = 4 * (size_t)S_pad * 128 + 3 * S_pad * 4 + 8 * 16 * STG_STRIDE;
   static bool attr = false;

@@ -211,6 +211,269 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   }
 }
 
+// ------------------------------------------------------------------------------------------ backward (2 x 2 tiles)
+// 1 control warp + 8 compute warps (two per TMEM lane quarter, splitting the 128 keys of a tile in halves).
+// smem: sQ[2] | sdO[2] | sK | sV | sP[2] | sdS[2] | sdQ[2] | mask[256] | lse2[256] | D[256] | barriers  (~195 KB)
+// TMEM: S [0,128) dP [128,256) dV [256,320) dK [320,384) dQ [384,448)
+constexpr int B2_CT = 256;
+constexpr int B2_THREADS = 32 + B2_CT;
+constexpr int B2_SMEM = 12 * TILE_BYTES + 3 * 256 * 4 + 128 + 1024;
+
+template <bool DROP>
+__global__ void __launch_bounds__(B2_THREADS, 1)
+attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_dctx,
+                    const __grid_constant__ CUtensorMap tm_dqkv, const int32_t* __restrict__ attn_mask,
+                    const float* __restrict__ lse_in, const bf16* __restrict__ ctx, const bf16* __restrict__ dctx,
+                    int S, int heads, int nseq, Drop drop) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                      // 2 tiles
+  uint8_t* sdO = sQ + 2 * TILE_BYTES;      // 2 tiles
+  uint8_t* sK = sdO + 2 * TILE_BYTES;      // key tile j
+  uint8_t* sV = sK + TILE_BYTES;
+  uint8_t* sP = sV + TILE_BYTES;           // [i 128][j 128] as 2 blocks of 64 columns
+  uint8_t* sdS = sP + 2 * TILE_BYTES;
+  uint8_t* sdQ = sdS + 2 * TILE_BYTES;     // 2 tiles: dQ_i summed over the key tiles (bf16)
+  float* sMask = reinterpret_cast<float*>(sdQ + 2 * TILE_BYTES);  // [256]
+  float* sLse = sMask + 256;                                      // [256] log2-domain LSE (+inf beyond S)
+  float* sD = sLse + 256;                                         // [256] D_i = rowsum(dO_i * O_i)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 256);
+  uint64_t *b_q = bars, *b_kv = bars + 1, *b_s = bars + 2, *b_p = bars + 3, *b_o = bars + 4, *b_kvfree = bars + 5,
+           *b_free = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = heads * 64;
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_qkv);
+      tma_prefetch_desc(&tm_dctx);
+      tma_prefetch_desc(&tm_dqkv);
+      mbar_init(b_q, 1); mbar_init(b_kv, 1); mbar_init(b_s, 1); mbar_init(b_p, 8); mbar_init(b_o, 1);
+      mbar_init(b_kvfree, 1); mbar_init(b_free, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 320, tdQ = tmem + 384;
+  const int nprob = nseq * heads;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16_f32(128, 128, 0, 0);
+      constexpr uint32_t idesc_t = make_idesc_bf16_f32(128, 64, 1, 1);
+      constexpr uint32_t idesc_q = make_idesc_bf16_f32(128, 64, 0, 1);
+      uint32_t ph = 0;    // per problem: b_q, b_free
+      uint32_t kvp = 0;   // per key tile: b_kv, b_kvfree
+      uint32_t sp = 0;    // per (j, i) step: b_s, b_p, b_o
+      for (int prob = blockIdx.x; prob < nprob; prob += gridDim.x) {
+        const int seq = prob / heads, h = prob - seq * heads;
+        mbar_wait(b_free, ph ^ 1);  // previous problem: every MMA retired, every staged tile stored
+        mbar_arrive_expect_tx(b_q, 4 * TILE_BYTES);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          tma_load_3d(sQ + t * TILE_BYTES, &tm_qkv, b_q, h * 64, t * 128, seq);
+          tma_load_3d(sdO + t * TILE_BYTES, &tm_dctx, b_q, h * 64, t * 128, seq);
+        }
+        for (int j = 0; j < 2; ++j) {
+          mbar_wait(b_kvfree, kvp ^ 1);  // dK / dV of the previous key tile have left sK / sV
+          mbar_arrive_expect_tx(b_kv, 2 * TILE_BYTES);
+          tma_load_3d(sK, &tm_qkv, b_kv, H + h * 64, j * 128, seq);
+          tma_load_3d(sV, &tm_qkv, b_kv, 2 * H + h * 64, j * 128, seq);
+          if (j == 0) mbar_wait(b_q, ph);
+          mbar_wait(b_kv, kvp);
+          tcgen05_fence_after();
+          const uint64_t dk = desc_kmajor(smem_u32(sK)), dv = desc_kmajor(smem_u32(sV));
+          const uint64_t bk = desc_mnmajor(smem_u32(sK), 0);
+          const uint64_t dpt = desc_mnmajor(smem_u32(sP), TILE_BYTES), dst = desc_mnmajor(smem_u32(sdS), TILE_BYTES);
+          for (int i = 0; i < 2; ++i) {
+            const uint64_t dq = desc_kmajor(smem_u32(sQ + i * TILE_BYTES)), ddo = desc_kmajor(smem_u32(sdO + i * TILE_BYTES));
+            const uint64_t bq = desc_mnmajor(smem_u32(sQ + i * TILE_BYTES), 0), bdo = desc_mnmajor(smem_u32(sdO + i * TILE_BYTES), 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(tS, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(tdP, ddo + 2 * k, dv + 2 * k, idesc_s, k > 0);
+            umma_commit(b_s);
+            mbar_wait(b_p, sp);
+            tcgen05_fence_after();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) umma_f16(tdV, dpt + 128 * k, bdo + 128 * k, idesc_t, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) umma_f16(tdK, dst + 128 * k, bq + 128 * k, idesc_t, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint64_t a = desc_kmajor(smem_u32(sdS + (k >> 2) * TILE_BYTES)) + 2 * (k & 3);
+              umma_f16(tdQ, a, bk + 128 * k, idesc_q, k > 0);
+            }
+            umma_commit(b_o);
+            if (i == 1) mbar_wait(b_o, sp);  // observer: all MMAs reading sK / sV of this key tile have retired
+            sp ^= 1;
+          }
+          kvp ^= 1;
+        }
+        ph ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    const int tid = threadIdx.x - 32;            // 0..255
+    const int cw = warp - 1;
+    const int quarter = warp & 3;
+    const int half = cw >> 2;
+    const int row = quarter * 32 + lane;         // row inside a 128-row tile
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    uint32_t sp = 0;
+    for (int prob = blockIdx.x; prob < nprob; prob += gridDim.x) {
+      const int seq = prob / heads, h = prob - seq * heads;
+      named_bar_sync(1, B2_CT);
+      {
+        const int r = tid;  // one sequence row per thread
+        const bool keep = r < S && (attn_mask == nullptr || attn_mask[(long long)seq * S + r] != 0);
+        sMask[r] = keep ? 0.f : -INFINITY;
+        sLse[r] = r < S ? lse_in[((long long)seq * heads + h) * S + r] * LOG2E : INFINITY;
+        float d = 0.f;
+        if (r < S) {
+          const long long off = ((long long)seq * S + r) * H + h * 64;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 a = *reinterpret_cast<const uint4*>(dctx + off + c * 8), b = *reinterpret_cast<const uint4*>(ctx + off + c * 8);
+            const uint32_t* pa = &a.x; const uint32_t* pb = &b.x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 x = unpack_bf16x2(pa[k]), y = unpack_bf16x2(pb[k]);
+              d = fmaf(x.x, y.x, d); d = fmaf(x.y, y.y, d);
+            }
+          }
+        }
+        sD[r] = d;
+      }
+      named_bar_sync(1, B2_CT);
+      for (int j = 0; j < 2; ++j) {
+        for (int i = 0; i < 2; ++i) {
+          const int grow = i * 128 + row;
+          const float lse2 = sLse[grow], D = sD[grow];
+          mbar_wait(b_s, sp);
+          tcgen05_fence_after();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t rs[32], rd[32];
+            tmem_ld_32x32(tS + lane_addr + half * 64 + c * 32, rs);
+            tmem_ld_32x32(tdP + lane_addr + half * 64 + c * 32, rd);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              float p[8], pd[8], ds[8];
+#pragma unroll
+              for (int t = 0; t < 8; ++t) {
+                const int jj = c4 * 8 + t;
+                p[t] = ex2_approx(fmaf(__uint_as_float(rs[jj]), SCALE_LOG2, sMask[j * 128 + half * 64 + c * 32 + jj]) - lse2);
+                pd[t] = p[t];
+                ds[t] = __uint_as_float(rd[jj]);
+              }
+              if (DROP) {
+#pragma unroll
+                for (int t = 0; t < 8; t += 2) {
+                  float m0, m1;
+                  drop.mul2((uint32_t)(prob * S + grow), (uint32_t)(j * 128 + half * 64 + c * 32 + c4 * 8 + t), m0, m1);
+                  pd[t] *= m0; pd[t + 1] *= m1;
+                  ds[t] *= m0; ds[t + 1] *= m1;
+                }
+              }
+#pragma unroll
+              for (int t = 0; t < 8; ++t) ds[t] = p[t] * (ds[t] - D);
+              const int chunk = c * 4 + c4;
+              st_chunk(sP + half * TILE_BYTES, row, chunk, pd, 1.f);
+              st_chunk(sdS + half * TILE_BYTES, row, chunk, ds, 0.125f);
+            }
+          }
+          fence_proxy_async_smem();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(b_p);
+          mbar_wait(b_o, sp);
+          tcgen05_fence_after();
+          {
+            // dQ_i += dS_ij K_j : this thread owns columns [32*half, +32) of its row; partial sums live in smem (bf16)
+            uint32_t r[32];
+            tmem_ld_32x32(tdQ + lane_addr + half * 32, r);
+            tmem_ld_wait();
+            uint8_t* acc = sdQ + i * TILE_BYTES;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              float v[8];
+#pragma unroll
+              for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(r[c4 * 8 + t]);
+              const int chunk = half * 4 + c4;
+              if (j > 0) {
+                const uint4 q = *reinterpret_cast<const uint4*>(acc + row * 128 + ((chunk ^ (row & 7)) << 4));
+                const uint32_t* pq = &q.x;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float2 f = unpack_bf16x2(pq[t]);
+                  v[2 * t] += f.x; v[2 * t + 1] += f.y;
+                }
+              }
+              st_chunk(acc, row, chunk, v, 1.f);
+            }
+          }
+          if (i == 1) {
+            // dK_j, dV_j are complete (accumulated over both query tiles): stage into sK / sV (dead: the control thread
+            // observed b_o of this step before it may reload them) and store
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+              uint32_t r[32];
+              tmem_ld_32x32((which == 0 ? tdK : tdV) + lane_addr + half * 32, r);
+              tmem_ld_wait();
+              uint8_t* dst = which == 0 ? sK : sV;
+#pragma unroll
+              for (int c4 = 0; c4 < 4; ++c4) {
+                float v[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(r[c4 * 8 + t]);
+                st_chunk(dst, row, half * 4 + c4, v, 1.f);
+              }
+            }
+            fence_proxy_async_smem();
+            tcgen05_fence_before();
+            named_bar_sync(2, B2_CT);
+            if (tid == 0) {
+              tma_store_3d(&tm_dqkv, smem_u32(sK), H + h * 64, j * 128, seq);
+              tma_store_3d(&tm_dqkv, smem_u32(sV), 2 * H + h * 64, j * 128, seq);
+              tma_store_commit();
+              tma_store_wait_read();
+              mbar_arrive(b_kvfree);
+            }
+          }
+          tcgen05_fence_before();
+          sp ^= 1;
+        }
+      }
+      // dQ of both query tiles
+      fence_proxy_async_smem();
+      named_bar_sync(2, B2_CT);
+      if (tid == 0) {
+        tma_store_3d(&tm_dqkv, smem_u32(sdQ), h * 64, 0, seq);
+        tma_store_3d(&tm_dqkv, smem_u32(sdQ + TILE_BYTES), h * 64, 128, seq);
+        tma_store_commit();
+        tma_store_wait_read();
+        mbar_arrive(b_free);
+      }
+    }
+    if (tid == 0) tma_store_wait_all();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -264,6 +527,34 @@ int attn_fwd_tc2(const void* qkv, const int32_t* attn_mask, void* ctx, float* ls
   const int grid = nprob < sms ? nprob : sms;
   if (drop.on()) attn_fwd_tc2_kernel<true><<<grid, F2_THREADS, F2_SMEM, stream>>>(tq, tc, attn_mask, lse, S, heads, nseq, drop);
   else attn_fwd_tc2_kernel<false><<<grid, F2_THREADS, F2_SMEM, stream>>>(tq, tc, attn_mask, lse, S, heads, nseq, drop);
+  DPRB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int attn_bwd_tc2(const void* qkv, const int32_t* attn_mask, const void* ctx, const float* lse, const void* dctx,
+                 void* dqkv, int nseq, int S, int heads, float dropout_p, unsigned long long site_seed,
+                 cudaStream_t stream) {
+  DPRB_REQUIRE(S > 128 && S <= 256, "attn_bwd_tc2: S=%d outside (128, 256]", S);
+  const Drop drop = drop_from_site(dropout_p, site_seed);
+  const int H = heads * 64;
+  CUtensorMap tq, tdo, tdq;
+  if (int rc = make_tmap3b(&tq, qkv, nseq, S, 3LL * H)) return rc;
+  if (int rc = make_tmap3b(&tdo, dctx, nseq, S, H)) return rc;
+  if (int rc = make_tmap3b(&tdq, dqkv, nseq, S, 3LL * H)) return rc;
+  static bool attr = false;
+  if (!attr) {
+    DPRB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM));
+    DPRB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM));
+    attr = true;
+  }
+  int sms = num_sms();
+  if (sms <= 0) sms = 148;
+  const int nprob = nseq * heads;
+  const int grid = nprob < sms ? nprob : sms;
+  if (drop.on())
+    attn_bwd_tc2_kernel<true><<<grid, B2_THREADS, B2_SMEM, stream>>>(tq, tdo, tdq, attn_mask, lse, (const bf16*)ctx, (const bf16*)dctx, S, heads, nseq, drop);
+  else
+    attn_bwd_tc2_kernel<false><<<grid, B2_THREADS, B2_SMEM, stream>>>(tq, tdo, tdq, attn_mask, lse, (const bf16*)ctx, (const bf16*)dctx, S, heads, nseq, drop);
   DPRB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -41,6 +41,9 @@ int attn_fwd_tc(const void* qkv, const int32_t* attn_mask, void* ctx, float* lse
                 float dropout_p, unsigned long long site_seed, cudaStream_t stream);
 int attn_fwd_tc2(const void* qkv, const int32_t* attn_mask, void* ctx, float* lse, int nseq, int S, int heads,
                  float dropout_p, unsigned long long site_seed, cudaStream_t stream);
+int attn_bwd_tc2(const void* qkv, const int32_t* attn_mask, const void* ctx, const float* lse, const void* dctx,
+                 void* dqkv, int nseq, int S, int heads, float dropout_p, unsigned long long site_seed,
+                 cudaStream_t stream);
 int attn_bwd_tc(const void* qkv, const int32_t* attn_mask, const float* lse, const void* dctx, void* dqkv,
                 float* dbias, int nseq, int S, int heads, float dropout_p, unsigned long long site_seed,
                 cudaStream_t stream);

@@ -166,7 +166,7 @@ def check_colsum(T=1000, N=2304, seed=3):
 
 
 # ------------------------------------------------------------------ attention
-def check_attention(nseq=3, S=128, heads=2, masked=True, seed=4):
+def check_attention(nseq=3, S=128, heads=2, masked=True, seed=4, dropout=0.0):
     g = torch.Generator().manual_seed(seed)
     H = heads * 64
     T = nseq * S
@@ -177,7 +177,13 @@ def check_attention(nseq=3, S=128, heads=2, masked=True, seed=4):
             ln = int(torch.randint(max(1, S // 4), S + 1, (1,), generator=g))
             am[i, ln:] = 0
     res = {}
-    ctx, lse = ops.attn_fwd(qkv.to(DEV), am.to(DEV) if masked else None, nseq, S, heads)
+    dseed, site = 0x1234567, 0
+    keepm = None
+    if dropout > 0:  # attention-probability dropout: export the (never stored) mask and replay it in the oracle
+        site = ops.dropout_site_seed(dseed, 3, 1)
+        keepm = ops.dropout_mask(nseq * heads * S, S, dropout, dseed, 3, 1).view(nseq, heads, S, S).float().cpu()
+        keepm = keepm / (1.0 - round(dropout * 65536) / 65536.0)
+    ctx, lse = ops.attn_fwd(qkv.to(DEV), am.to(DEV) if masked else None, nseq, S, heads, True, dropout, site)
     qr = qkv.float().requires_grad_(True)
     x = qr.view(nseq, S, 3, heads, 64)
     q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))  # nseq, heads, S, 64
@@ -185,12 +191,15 @@ def check_attention(nseq=3, S=128, heads=2, masked=True, seed=4):
     if masked:
         sc = sc.masked_fill(am.view(nseq, 1, 1, S) == 0, float("-inf"))
     p = torch.softmax(sc, -1)
+    if keepm is not None:
+        p = p * keepm
     cr = (p @ v).transpose(1, 2).reshape(T, H)
     _close("attn_ctx", ctx, cr, 2 ** -7, 2e-3, res)
     _close("attn_lse", lse, torch.logsumexp(sc, -1), 1e-4, 1e-3, res)
     dctx = _bf(torch.randn(T, H, generator=g))
     dbias = torch.ones(3 * H, device=DEV)
-    dqkv = ops.attn_bwd(qkv.to(DEV), am.to(DEV) if masked else None, ctx, lse, dctx.to(DEV), nseq, S, heads, dbias)
+    dqkv = ops.attn_bwd(qkv.to(DEV), am.to(DEV) if masked else None, ctx, lse, dctx.to(DEV), nseq, S, heads, dbias,
+                        dropout, site)
     cr.backward(dctx.float())
     # P and dS are rounded to bf16 before the second matmuls (as in any flash-style kernel): 2^-6 headroom
     _close("attn_dqkv", dqkv, qr.grad, 2 ** -6, 4e-3, res)
@@ -282,3 +291,5 @@ CHECKS["attn_tc_s64_many"] = lambda: check_attention(33, 64, 4, True, seed=10)
 CHECKS["attn_tc_s37"] = lambda: check_attention(5, 37, 2, True, seed=11)
 CHECKS["attn_tc2_s200"] = lambda: check_attention(3, 200, 2, True, seed=12)
 CHECKS["attn_tc2_s256_many"] = lambda: check_attention(20, 256, 4, True, seed=13)
+CHECKS["attn_tc_drop_s128"] = lambda: check_attention(4, 128, 2, True, seed=14, dropout=0.1)
+CHECKS["attn_tc2_drop_s200"] = lambda: check_attention(3, 200, 2, True, seed=15, dropout=0.1)

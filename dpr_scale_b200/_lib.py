@@ -74,6 +74,10 @@ SIGNATURES = {
     "dprb_encoder_workspace_bytes": (c_int64, [POINTER(EncoderWeights), c_int, c_int, c_int]),
     "dprb_encoder_fwd": (c_int, [POINTER(EncoderWeights), POINTER(EncoderBatch), _P, _P]),
     "dprb_encoder_bwd": (c_int, [POINTER(EncoderWeights), POINTER(EncoderBatch), _P, c_int, c_int, _P]),
+    "dprb_search_workspace_bytes": (c_int64, [c_int64, c_int]),
+    "dprb_search_topk": (c_int, [_P, _P, c_int, c_int64, c_int64, c_int, c_int, c_int64, _P, _P, _P, c_int64, _P]),
+    "dprb_topk_merge_workspace_bytes": (c_int64, [c_int64, c_int]),
+    "dprb_topk_merge": (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P, _P, c_int64, _P]),
 }
 
 _lib = None

@@ -132,5 +132,18 @@ int dprb_encoder_bwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b,
                      int layer_lo, int layer_hi, dprb_stream_t stream) {
   return encoder_bwd(w, b, dpooled, layer_lo, layer_hi, S(stream));
 }
+int64_t dprb_search_workspace_bytes(int64_t Q, int k) { return search_workspace_bytes(Q, k); }
+int dprb_search_topk(const void* queries, const void* corpus, int dtype, int64_t Q, int64_t N, int d, int k,
+                     int64_t index_offset, float* out_scores, int64_t* out_index, void* workspace,
+                     int64_t workspace_bytes, dprb_stream_t stream) {
+  return search_topk(queries, corpus, dtype, Q, N, d, k, index_offset, out_scores,
+                     reinterpret_cast<long long*>(out_index), workspace, workspace_bytes, S(stream));
+}
+int64_t dprb_topk_merge_workspace_bytes(int64_t Q, int total) { return topk_merge_workspace_bytes(Q, total); }
+int dprb_topk_merge(const float* scores, const int64_t* index, int64_t Q, int total, int k, float* out_scores,
+                    int64_t* out_index, void* workspace, int64_t workspace_bytes, dprb_stream_t stream) {
+  return topk_merge(scores, reinterpret_cast<const long long*>(index), Q, total, k, out_scores,
+                    reinterpret_cast<long long*>(out_index), workspace, workspace_bytes, S(stream));
+}
 
 }  // extern "C"

@@ -67,6 +67,14 @@ int adamw_step(float* p, const float* g, float* m, float* v, void* shadow, long 
                cudaStream_t stream);
 int cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t stream);
 
+long long search_workspace_bytes(long long Q, int k);
+int search_topk(const void* queries, const void* corpus, int dtype, long long Q, long long N, int d, int k,
+                long long index_offset, float* out_scores, long long* out_index, void* workspace,
+                long long workspace_bytes, cudaStream_t stream);
+long long topk_merge_workspace_bytes(long long Q, int total);
+int topk_merge(const float* scores, const long long* index, long long Q, int total, int k, float* out_scores,
+               long long* out_index, void* workspace, long long workspace_bytes, cudaStream_t stream);
+
 long long encoder_workspace_bytes(const dprb_encoder_weights* w, int nseq, int S, int save);
 int encoder_fwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b, float* pooled, cudaStream_t stream);
 int encoder_bwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b, const float* dpooled, int layer_lo,

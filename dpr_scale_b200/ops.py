@@ -180,3 +180,48 @@ def cast_f32_bf16(src, dst):
     check(_lib.load().dprb_cast_f32_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()), "dprb_cast_f32_bf16")
     _count()
     return dst
+
+
+_SEARCH_WS = {}
+
+
+def _search_ws(nbytes, device):
+    """Caller-owned workspace, cached per device and grown on demand (queues are reused across calls)."""
+    buf = _SEARCH_WS.get(device)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _SEARCH_WS[device] = buf
+    return buf
+
+
+def search_topk(queries, corpus, k, index_offset=0):
+    """Fused inner-product search + top-k: queries [Q, d], corpus [N, d] (both fp16 or both bf16, contiguous)
+    -> (scores fp32 [Q, k] descending, row ids int64 [Q, k]); never materialises the [Q, N] score matrix."""
+    assert queries.dtype == corpus.dtype and queries.dtype in (torch.float16, torch.bfloat16)
+    assert queries.is_contiguous() and corpus.is_contiguous() and queries.shape[1] == corpus.shape[1]
+    lib = _lib.load()
+    Q, d = queries.shape
+    N = corpus.shape[0]
+    ws = _search_ws(lib.dprb_search_workspace_bytes(Q, int(k)), queries.device)
+    scores = torch.empty(Q, k, dtype=torch.float32, device=queries.device)
+    index = torch.empty(Q, k, dtype=torch.int64, device=queries.device)
+    check(lib.dprb_search_topk(_ptr(queries), _ptr(corpus), 1 if queries.dtype == torch.bfloat16 else 0, Q, N, d,
+                               int(k), int(index_offset), _ptr(scores), _ptr(index), _ptr(ws), ws.numel(),
+                               _stream()), "dprb_search_topk")
+    _count(2 * ((Q + 1023) // 1024))
+    return scores, index
+
+
+def topk_merge(scores, index, k):
+    """k best of each row of scores [Q, total] fp32 with their index [Q, total] int64 entries (shard merge)."""
+    assert scores.dtype == torch.float32 and index.dtype == torch.int64 and scores.shape == index.shape
+    assert scores.is_contiguous() and index.is_contiguous()
+    lib = _lib.load()
+    Q, total = scores.shape
+    ws = torch.empty(int(lib.dprb_topk_merge_workspace_bytes(Q, total)), dtype=torch.uint8, device=scores.device)
+    out_s = torch.empty(Q, k, dtype=torch.float32, device=scores.device)
+    out_i = torch.empty(Q, k, dtype=torch.int64, device=scores.device)
+    check(lib.dprb_topk_merge(_ptr(scores), _ptr(index), Q, total, int(k), _ptr(out_s), _ptr(out_i), _ptr(ws),
+                              ws.numel(), _stream()), "dprb_topk_merge")
+    _count(2)
+    return out_s, out_i

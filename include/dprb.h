@@ -201,6 +201,28 @@ int dprb_encoder_fwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b,
 int dprb_encoder_bwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b, const float* dpooled,
                      int layer_lo, int layer_hi, dprb_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Brute-force retrieval: replaces search_index() of
+ * dpr_scale/run_retrieval_pytorch.py:141-176 -- einsum('ik,jk->ij') in fp16 followed by torch.topk over the
+ * materialised [Q, N] score matrix -- with one fused pass: the corpus is streamed once per block of 128 queries
+ * through tcgen05 and a running top-k is kept per query; no score matrix is written.
+ *   queries [Q, d], corpus [N, d]: row-major 16-bit (dtype 0 = fp16 as in build_index() :178-190, 1 = bf16),
+ *   d % 8 == 0, 16-byte aligned, N < 2^31 - 256, 1 <= k <= min(N, 1024).
+ *   out_scores [Q, k] fp32 (fp32-accumulated inner products, descending; ties towards the lower row id),
+ *   out_index  [Q, k] int64 = corpus row id + index_offset (the shard offset of :225-227).
+ *   workspace: >= dprb_search_workspace_bytes(Q, k) bytes of device memory, caller-owned.
+ * dprb_topk_merge replaces the per-shard merge of :272-277 (topk over the concatenated shard results + gather):
+ *   scores / index [Q, total] -> the k best per row (ties towards the earlier position), workspace
+ *   >= dprb_topk_merge_workspace_bytes(Q, total).
+ * ------------------------------------------------------------------------------------------- */
+int64_t dprb_search_workspace_bytes(int64_t Q, int k);
+int dprb_search_topk(const void* queries, const void* corpus, int dtype, int64_t Q, int64_t N, int d, int k,
+                     int64_t index_offset, float* out_scores, int64_t* out_index, void* workspace,
+                     int64_t workspace_bytes, dprb_stream_t stream);
+int64_t dprb_topk_merge_workspace_bytes(int64_t Q, int total);
+int dprb_topk_merge(const float* scores, const int64_t* index, int64_t Q, int total, int k, float* out_scores,
+                    int64_t* out_index, void* workspace, int64_t workspace_bytes, dprb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -293,3 +293,98 @@ CHECKS["attn_tc2_s200"] = lambda: check_attention(3, 200, 2, True, seed=12)
 CHECKS["attn_tc2_s256_many"] = lambda: check_attention(20, 256, 4, True, seed=13)
 CHECKS["attn_tc_drop_s128"] = lambda: check_attention(4, 128, 2, True, seed=14, dropout=0.1)
 CHECKS["attn_tc2_drop_s200"] = lambda: check_attention(3, 200, 2, True, seed=15, dropout=0.1)
+
+
+# ------------------------------------------------------------------ retrieval
+def check_search(Q=100, N=5000, d=768, k=100, bf16=False, seed=20, mode="random", offset=0):
+    """dprb_search_topk vs oracle/retrieval.py (restating run_retrieval_pytorch.py:141-176) on float64 scores.
+
+    Tolerance: the kernel ranks by fp32-accumulated products of the identical 16-bit operands, so a returned score
+    may differ from the float64 score of the same row by tol = 1e-5 * max_row(|q|.|c|); ids must agree with the
+    oracle wherever scores are separated by more than 2 tol, and the returned set must be a valid top-k up to 2 tol.
+    """
+    import numpy as np
+    from oracle import retrieval as R
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randn(Q, d, generator=g)
+    if mode == "random":
+        c = torch.randn(N, d, generator=g)
+    elif mode == "dup":          # every row appears twice -> exact score ties, resolved towards the lower id
+        h = torch.randn((N + 1) // 2, d, generator=g)
+        c = torch.cat([h, h], 0)[:N]
+    elif mode == "ascending":    # scores grow with the row id for every query: worst case for the running threshold
+        v = torch.randn(d, generator=g)
+        q = q * 0.05 + v
+        c = v[None, :] * (0.25 + torch.arange(N, dtype=torch.float32)[:, None] / N)
+    elif mode == "constant":     # every row identical: all scores tie, the answer is rows 0..k-1 for every query
+        c = torch.randn(1, d, generator=g).expand(N, d).contiguous()
+    else:
+        raise ValueError(mode)
+    dt = torch.bfloat16 if bf16 else torch.float16
+    q16, c16 = q.to(dt), c.to(dt)
+    s, i = ops.search_topk(q16.to(DEV), c16.to(DEV), k, index_offset=offset)
+    torch.cuda.synchronize()
+    s, i = s.cpu().numpy().astype(np.float64), i.cpu().numpy() - offset
+    qe, ce = q16.double().numpy(), c16.double().numpy()
+    exact = qe @ ce.T
+    tol = 1e-5 * float((np.abs(qe) @ np.abs(ce).T).max())
+    out = {"tol": tol}
+    assert s.shape == (Q, k) and i.shape == (Q, k)
+    assert (i >= 0).all() and (i < N).all(), "row ids out of range"
+    assert all(len(set(r)) == k for r in i), "duplicate row ids"
+    ds = np.diff(s, axis=1)
+    assert (ds <= 0).all(), "scores not descending"
+    assert (np.diff(i, axis=1)[ds == 0] > 0).all(), "equal scores not ordered by ascending row id"
+    got = np.take_along_axis(exact, i, axis=1)
+    out["score_maxerr"] = float(np.abs(got - s).max())
+    assert out["score_maxerr"] <= tol, f"score error {out['score_maxerr']:.3e} > {tol:.3e}"
+    os_, oi = R.topk_desc(exact, min(k + 1, N))
+    kth = os_[:, k - 1]
+    assert (got >= kth[:, None] - 2 * tol).all(), "returned a row that is not in the top-k"
+    mism = 0
+    for r in range(Q):
+        must = oi[r, :k][os_[r, :k] > kth[r] + 2 * tol]
+        assert set(must) <= set(i[r]), f"query {r}: missing rows with score above the k-th"
+        e = os_[r]
+        for j in range(k):
+            lo = e[j] - e[j + 1] if j + 1 < len(e) else np.inf
+            hi = e[j - 1] - e[j] if j > 0 else np.inf
+            if lo > 2 * tol and hi > 2 * tol:
+                assert i[r, j] == oi[r, j], f"query {r} rank {j}: {i[r, j]} vs oracle {oi[r, j]}"
+            else:
+                mism += int(i[r, j] != oi[r, j])
+    out["near_tie_swaps"] = mism
+    return out
+
+
+def check_topk_merge(Q=37, total=300, k=100, seed=30):
+    """dprb_topk_merge vs the restated shard merge (run_retrieval_pytorch.py:272-277: topk over the concatenated shard
+    results + gather); bit-exact (fp32 compare / select only), ties towards the earlier position."""
+    import numpy as np
+    from oracle import retrieval as R
+    g = torch.Generator().manual_seed(seed)
+    s = torch.randn(Q, total, generator=g)
+    nt = min(s[:, ::7].shape[1], s[:, 3::7].shape[1])
+    s[:, 0:7 * nt:7] = s[:, 3:3 + 7 * nt:7]                  # inject exact ties
+    idx = torch.randint(0, 2 ** 40, (Q, total), generator=g, dtype=torch.int64)
+    ms, mi = ops.topk_merge(s.to(DEV), idx.to(DEV), k)
+    torch.cuda.synchronize()
+    rs, order = R.topk_desc(s.numpy().astype(np.float64), k)
+    ri = np.take_along_axis(idx.numpy(), order, axis=1)
+    assert np.array_equal(ms.cpu().numpy().astype(np.float64), rs), "merged scores differ"
+    assert np.array_equal(mi.cpu().numpy(), ri), "merged ids differ"
+    return {"exact": True}
+
+
+CHECKS["search_fp16_100x5000"] = lambda: check_search(100, 5000, 768, 100)
+CHECKS["search_small_ragged"] = lambda: check_search(7, 1000, 200, 10, seed=21)
+CHECKS["search_k_equals_n_region"] = lambda: check_search(5, 300, 64, 256, seed=22)
+CHECKS["search_one_query_k1"] = lambda: check_search(1, 4097, 128, 1, seed=23)
+CHECKS["search_bf16_300x70000"] = lambda: check_search(300, 70000, 1024, 256, bf16=True, seed=24, offset=1000000)
+CHECKS["search_many_query_tiles"] = lambda: check_search(1100, 30000, 256, 100, seed=25)
+CHECKS["search_k1000"] = lambda: check_search(40, 60000, 128, 1000, seed=26)
+CHECKS["search_duplicate_rows"] = lambda: check_search(33, 9000, 128, 50, seed=27, mode="dup")
+CHECKS["search_ascending_scores"] = lambda: check_search(64, 20000, 64, 100, seed=28, mode="ascending")
+CHECKS["search_all_equal"] = lambda: check_search(40, 5000, 64, 100, seed=29, mode="constant")
+CHECKS["topk_merge"] = lambda: check_topk_merge()
+CHECKS["topk_merge_large"] = lambda: check_topk_merge(Q=5, total=40000, k=1000, seed=31)

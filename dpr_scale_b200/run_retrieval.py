@@ -1,0 +1,218 @@
+#!/usr/bin/env python3
+"""Brute-force retrieval over the ``reps_*`` files written by GenerateEmbeddingsTask - the B200 counterpart of
+/root/reference/dpr_scale/run_retrieval_pytorch.py (same command line, same output files).
+
+What changes under the hood:
+  * search_index (:141-176) is ONE fused kernel pass per 1024 queries (ops.search_topk: tcgen05 scoring with a
+    running top-k); the [batch, N] fp16 score matrix and the torch.topk passes over it are gone, so ``--batch`` no
+    longer bounds memory (it is accepted and ignored).
+  * an index segment is held in HBM as fp16 exactly like build_index (:178-190); with 180 GB per GPU the 21 M x 768
+    Wikipedia index (32 GB) is one segment.  ``--shard`` still splits the reps_* files into sequential segments and
+    the per-segment lists are merged on the GPU (ops.topk_merge, replacing :210-230 / :272-277).
+  * scores are rounded to fp16 before they are written, because the reference's scores are fp16 einsum outputs;
+    ``--fp32_scores`` keeps the fp32-accumulated values instead.
+
+There is no CPU path: without the CUDA library the ops raise DprbError.
+"""
+import argparse
+import ast
+import glob
+import json
+import logging
+import os
+import pathlib
+import pickle
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def get_logger():
+    logging.basicConfig(format="[%(asctime)s] [%(levelname)s]: %(message)s", level=logging.INFO)
+    return logging.getLogger(__name__)
+
+
+def get_parser():
+    p = argparse.ArgumentParser()
+    p.add_argument("--ctx_embeddings_dir", type=str, default="")
+    p.add_argument("--query_emb_path", type=str, default="",
+                   help="if left empty, will use <ctx_embeddings_dir>/query_reps.pkl")
+    p.add_argument("--questions_tsv_path", type=str, default="")
+    p.add_argument("--passages_tsv_path", type=str, default="")
+    p.add_argument("--output_runfile_path", type=str, default="")
+    p.add_argument("--topk", type=int, default=100)
+    p.add_argument("--batch", type=int, default=100, help="accepted for compatibility; the fused search ignores it")
+    p.add_argument("--shard", type=int, default=1)
+    p.add_argument("--trec_format", action="store_true")
+    p.add_argument("--run_name", type=str, default="dpr")
+    p.add_argument("--ignore_identical_ids", action="store_true",
+                   help="this is used for BEIR Arguana and Quora datasets")
+    p.add_argument("--fp32_scores", action="store_true", help="write fp32 scores instead of fp16-rounded ones")
+    return p
+
+
+# ------------------------------------------------------------------ tab-separated inputs (datamodule/dpr.py:80-159)
+def _unquote(line, sep="\t"):
+    row = line.rstrip("\r\n").split(sep)
+    return [v.strip('"').replace('""', '"') if v and v[0] == '"' and v[-1] == '"' else v for v in row]
+
+
+class TableFile:
+    """Random access to the rows of a tab-separated file through a byte-offset table (rows stay on disk)."""
+
+    def __init__(self, path, header):
+        self.path = path
+        self._f = open(path, "rb")
+        offsets, pos = [], 0
+        for line in self._f:
+            offsets.append(pos)
+            pos += len(line)
+        self.columns = None
+        if header and offsets:
+            self.columns = self.row(offsets[0])
+            offsets = offsets[1:]
+        self._offsets = offsets
+
+    def row(self, offset):
+        self._f.seek(offset)
+        return _unquote(self._f.readline().decode())
+
+    def __len__(self):
+        return len(self._offsets)
+
+    def __getitem__(self, i):
+        return self.parse(self.row(self._offsets[int(i)]))
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def parse(self, vals):
+        return vals
+
+
+class Passages(TableFile):
+    """id / text / title table with a header row (CSVDataset, datamodule/dpr.py:80-107)."""
+
+    def __init__(self, path):
+        super().__init__(path, header=True)
+
+    def parse(self, vals):
+        if len(vals) != len(self.columns):
+            return self[0]                       # the reference falls back to row 0 on malformed lines
+        return dict(zip(self.columns, vals))
+
+
+class Questions(TableFile):
+    """question \\t answers (QueryCSVDataset :110-134) or, for trec, qid \\t question (QueryTSVDataset :137-159)."""
+
+    def __init__(self, path, trec_format):
+        super().__init__(path, header=False)
+        self.trec_format = trec_format
+
+    def parse(self, vals):
+        if self.trec_format:
+            return {"id": vals[0], "question": vals[1]}
+        return {"question": vals[0], "answers": ast.literal_eval(vals[1])}
+
+
+# ------------------------------------------------------------------ search
+def build_index(paths, device="cuda"):
+    """fp16 index segment in HBM from reps_* pickles (build_index, run_retrieval_pytorch.py:178-190)."""
+    parts = []
+    for fname in paths:
+        with open(fname, "rb") as f:
+            vector = torch.as_tensor(pickle.load(f))
+        parts.append(vector.to(device=device, dtype=torch.float16, non_blocking=True))
+        print(f"Adding {tuple(vector.shape)} vectors from {fname}")
+    return torch.cat(parts, dim=0) if len(parts) > 1 else parts[0].contiguous()
+
+
+def search_index(query_embs, corpus_embs, batch, topk, index_offset=0):
+    """(scores [Q, k] fp32, row ids [Q, k] int64) on the GPU; argument meaning as run_retrieval_pytorch.py:141."""
+    del batch
+    q = torch.as_tensor(query_embs).to(device=corpus_embs.device, dtype=corpus_embs.dtype).contiguous()
+    return ops.search_topk(q, corpus_embs, topk, index_offset=index_offset)
+
+
+def search_segments(q_repr, input_paths, shard, batch, topk, device="cuda"):
+    """Search ``shard`` sequential index segments and merge (run_retrieval_pytorch.py:204-230, :272-277)."""
+    assert len(input_paths) % shard == 0, "Invalid Shard number"
+    per = len(input_paths) // shard
+    all_s, all_i, offset = [], [], 0
+    for seg in range(shard):
+        index = build_index(input_paths[seg * per:(seg + 1) * per], device)
+        s, i = search_index(q_repr, index, batch, topk, index_offset=offset)
+        offset += index.shape[0]
+        del index
+        all_s.append(s)
+        all_i.append(i)
+    if shard == 1:
+        return all_s[0], all_i[0]
+    return ops.topk_merge(torch.cat(all_s, dim=1).contiguous(), torch.cat(all_i, dim=1).contiguous(), topk)
+
+
+# ------------------------------------------------------------------ output (merge_results :96-137, writer :232-300)
+def merge_results(passages, questions, top_doc_ids, scores_list, trec_format):
+    assert len(top_doc_ids) == len(questions) == len(scores_list)
+    merged = []
+    for i, (question, doc_ids, scores) in enumerate(zip(questions, top_doc_ids, scores_list)):
+        ctxs = []
+        for doc, score in zip(doc_ids, scores):
+            try:
+                row = passages[doc]
+                if trec_format:
+                    ctxs.append({"id": row["id"], "score": float(score)})
+                else:
+                    ctxs.append({"id": row["id"], "title": row["title"], "text": row["text"], "score": float(score)})
+            except (KeyError, IndexError, TypeError):
+                if not trec_format:
+                    raise
+                continue                          # BEIR files contain empty lines; the reference skips them
+        merged.append({"question": question["question"], "answers": question.get("answers", []), "ctxs": ctxs,
+                       "id": question.get("id", i)})
+    return merged
+
+
+def write_run(path, passages, questions, scores, indexes, trec_format, run_name="dpr", ignore_identical_ids=False):
+    pathlib.Path(path).parent.mkdir(parents=True, exist_ok=True)
+    with open(path, "w") as g:
+        results = merge_results(passages, questions, indexes, scores, trec_format)
+        if not trec_format:
+            g.write(json.dumps(results, indent=4))
+            g.write("\n")
+            return
+        for result in results:
+            for rank, ctx in enumerate(result["ctxs"], start=1):
+                if ignore_identical_ids and result["id"] == ctx["id"]:
+                    continue
+                g.write("{} Q0 {} {} {} {}\n".format(result["id"], ctx["id"], rank, ctx["score"], run_name))
+
+
+def main(args, logger=None):
+    logger = logger or get_logger()
+    logger.info(args.__dict__)
+    input_paths = sorted(glob.glob(os.path.join(args.ctx_embeddings_dir, "reps_*")))
+    assert input_paths, f"no reps_* files under {args.ctx_embeddings_dir}"
+    qpath = args.query_emb_path or os.path.join(args.ctx_embeddings_dir, "query_reps.pkl")
+    print("Loading question vectors.")
+    with open(qpath, "rb") as f:
+        q_repr = torch.as_tensor(pickle.load(f))
+    print("Retrieving results...")
+    scores, indexes = search_segments(q_repr, input_paths, args.shard, args.batch, args.topk)
+    if not args.fp32_scores:
+        scores = scores.to(torch.float16)
+    scores = scores.float().cpu().numpy().astype(np.float64)
+    indexes = indexes.cpu().numpy()
+    print(f"Loading questions file {args.questions_tsv_path}")
+    questions = list(Questions(args.questions_tsv_path, args.trec_format))
+    print(f"Loading passages from {args.passages_tsv_path}")
+    passages = Passages(args.passages_tsv_path)
+    print(f"Writing output to {args.output_runfile_path}")
+    write_run(args.output_runfile_path, passages, questions, scores, indexes, args.trec_format, args.run_name,
+              args.ignore_identical_ids)
+
+
+if __name__ == "__main__":
+    main(get_parser().parse_args())

@@ -16,6 +16,7 @@
 // Ranking is by fp32-accumulated score, ties broken towards the lower index (torch.topk leaves tie order
 // unspecified).  Results are exact for the fp32 scores: no approximation, no score quantisation.
 #include <cstdint>
+#include <cstdlib>
 #include "common.cuh"
 #include "dprb_internal.h"
 
@@ -54,9 +55,15 @@ struct SearchParams {
   int* counts;          // [gridDim.x][gridDim.y * 128]
   uint32_t* bounds;     // [gridDim.x][gridDim.y * 128] ordered-uint of each partition's m-th best score (0 = none yet)
   int m_track;          // m = ceil(k / partitions) if <= 8, else 0 (cross-partition bound disabled)
+  int pf_ahead;         // corpus k-block boxes prefetched into L2 ahead of the shared-memory ring (0 = off)
   uint32_t idesc;
 };
 
+// TMA prefetch of one box into L2 (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ uint32_t ord_u32(float v) {   // monotone float -> unsigned
   const uint32_t u = __float_as_uint(v);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -188,11 +195,25 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   if (warp == 0) {
     // ---------------- TMA producer: query tile (L2-resident) + corpus tile (HBM stream) per k-block
     if (lane == 0) {
+      // Optional: pull corpus boxes into L2 pf_ahead k-blocks ahead of the 4-stage ring (DPRB_SEARCH_PF; measured
+      // slower than the plain ring on B200, so off by default).
       int stage = 0;
       uint32_t phase = 0;
+      const long long items = (t1 - t0) * p.kblocks;
+      long long pf = 0;                                    // next (tile, k-block) item to prefetch
+      int pf_kb = 0;
+      long long pf_t = t0;
+      auto prefetch_until = [&](long long upto) {
+        for (; pf < upto && pf < items; ++pf) {
+          tma_prefetch_l2_2d(&tm_c, pf_kb * BK, (int)(pf_t * CT));
+          if (++pf_kb == p.kblocks) { pf_kb = 0; ++pf_t; }
+        }
+      };
+      long long n = 0;
       for (long long t = t0; t < t1; ++t) {
         const int row0 = (int)(t * CT);
-        for (int kb = 0; kb < p.kblocks; ++kb) {
+        for (int kb = 0; kb < p.kblocks; ++kb, ++n) {
+          if (p.pf_ahead > 0) prefetch_until(n + p.pf_ahead);
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
           tma_load_2d(smem_a + stage * A_BYTES, &tm_q, &full_bar[stage], kb * BK, q0);
@@ -273,23 +294,29 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         tmem_ld_wait();
         const uint32_t ib = idx0 + c * 32;
         const int nvalid = ncols - c * 32;          // >= 32 except in the ragged last tile
+        // one test per 32 scores: in steady state almost no chunk holds a score above the bar
+        float cmax = __uint_as_float(r[0]);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float v = __uint_as_float(r[j]);
-          if (v >= lowbar && j < nvalid) {
-            if (v >= thr) myq[cnt++] = make_key(v, ib + j);
-            if (v > t7_) {
-              float x = v, y;                                            // insert, dropping the old 8th best
-              y = fminf(t0_, x); t0_ = fmaxf(t0_, x); x = y;
-              y = fminf(t1_, x); t1_ = fmaxf(t1_, x); x = y;
-              y = fminf(t2_, x); t2_ = fmaxf(t2_, x); x = y;
-              y = fminf(t3_, x); t3_ = fmaxf(t3_, x); x = y;
-              y = fminf(t4_, x); t4_ = fmaxf(t4_, x); x = y;
-              y = fminf(t5_, x); t5_ = fmaxf(t5_, x); x = y;
-              y = fminf(t6_, x); t6_ = fmaxf(t6_, x); x = y;
-              t7_ = fmaxf(t7_, x);
+        for (int j = 1; j < 32; ++j) cmax = fmaxf(cmax, __uint_as_float(r[j]));
+        if (cmax >= lowbar) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float v = __uint_as_float(r[j]);
+            if (v >= lowbar && j < nvalid) {
+              if (v >= thr) myq[cnt++] = make_key(v, ib + j);
+              if (v > t7_) {
+                float x = v, y;                                            // insert, dropping the old 8th best
+                y = fminf(t0_, x); t0_ = fmaxf(t0_, x); x = y;
+                y = fminf(t1_, x); t1_ = fmaxf(t1_, x); x = y;
+                y = fminf(t2_, x); t2_ = fmaxf(t2_, x); x = y;
+                y = fminf(t3_, x); t3_ = fmaxf(t3_, x); x = y;
+                y = fminf(t4_, x); t4_ = fmaxf(t4_, x); x = y;
+                y = fminf(t5_, x); t5_ = fmaxf(t5_, x); x = y;
+                y = fminf(t6_, x); t6_ = fmaxf(t6_, x); x = y;
+                t7_ = fmaxf(t7_, x);
+              }
+              lowbar = fminf(thr, t7_);
             }
-            lowbar = fminf(thr, t7_);
           }
         }
       }
@@ -308,6 +335,14 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         if (track && g > ord_u32(thr)) {
           thr = unord_u32(g);
           lowbar = fminf(thr, t7_);
+          // drop queued rows that fell below the new bound (thread-private pass; keeps the final lists short)
+          const u64 floor_key = (u64)g << 32;
+          uint32_t w = 0;
+          for (uint32_t i = 0; i < cnt; ++i) {
+            const u64 key = myq[i];
+            if (key >= floor_key) myq[w++] = key;
+          }
+          cnt = w;
         }
       }
     }
@@ -568,6 +603,10 @@ int search_topk(const void* queries, const void* corpus, int dtype, long long Q,
     sp.idesc = make_idesc16(QT, CT, dtype);
     const long long m = (k + parts - 1) / parts;
     sp.bounds = bounds;
+    {
+      const char* e = getenv("DPRB_SEARCH_PF");
+      sp.pf_ahead = e != nullptr ? atoi(e) : 0;
+    }
     sp.m_track = m <= 8 ? (int)m : 0;
     if (sp.m_track > 0)
       DPRB_CHECK_CUDA(cudaMemsetAsync(bounds, 0, (size_t)parts * nb * QT * sizeof(uint32_t), stream));

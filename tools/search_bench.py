@@ -46,7 +46,7 @@ def ref_search(q, corpus, batch, k):
     return torch.cat(outs), torch.cat(outi)
 
 
-def run(N, d, Q, k, iters=3):
+def run(N, d, Q, k, iters=10):
     dev = "cuda"
     g = torch.Generator(device=dev).manual_seed(0)
     corpus = torch.empty(N, d, dtype=torch.float16, device=dev)
@@ -55,12 +55,15 @@ def run(N, d, Q, k, iters=3):
         corpus[s:e] = torch.randn(e - s, d, generator=g, device=dev, dtype=torch.float32).to(torch.float16)
     q = torch.randn(Q, d, generator=g, device=dev, dtype=torch.float32).to(torch.float16)
     ms = timeit(lambda: ops.search_topk(q, corpus, k), iters)
-    ms_ref = timeit(lambda: ref_search(q, corpus, 100, k), max(1, iters - 1))     # --batch 100 is the reference default
-    s, i = ops.search_topk(q, corpus, k)
-    rs, ri = ref_search(q, corpus, 100, k)
-    # the reference ranks fp16-rounded scores; ours rounded the same way must be the same multiset per row
-    same_scores = float((s.to(torch.float16) == rs).float().mean())
-    same_ids = float((i == ri).float().mean())
+    if os.environ.get("SEARCH_BENCH_SKIP_REF"):
+        ms_ref, same_scores, same_ids = float("nan"), float("nan"), float("nan")
+    else:
+        ms_ref = timeit(lambda: ref_search(q, corpus, 100, k), max(1, iters - 1))  # --batch 100 is the reference default
+        s, i = ops.search_topk(q, corpus, k)
+        rs, ri = ref_search(q, corpus, 100, k)
+        # the reference ranks fp16-rounded scores; ours rounded the same way must be the same multiset per row
+        same_scores = float((s.to(torch.float16) == rs).float().mean())
+        same_ids = float((i == ri).float().mean())
     passes = (Q + 127) // 128
     peak, src = peak_gbs()
     gbs = passes * N * d * 2 / (ms * 1e-3) / 1e9

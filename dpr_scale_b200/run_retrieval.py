@@ -12,7 +12,8 @@ What changes under the hood:
   * scores are rounded to fp16 before they are written, because the reference's scores are fp16 einsum outputs;
     ``--fp32_scores`` keeps the fp32-accumulated values instead.
 
-There is no CPU path: without the CUDA library the ops raise DprbError.
+Under torchrun the index is sharded over the ranks (each GPU searches the reps_* block it owns; one all-gather of the
+[Q, k] lists; merge) - see search_distributed.  There is no CPU path: without the CUDA library the ops raise DprbError.
 """
 import argparse
 import ast
@@ -25,6 +26,7 @@ import pickle
 
 import numpy as np
 import torch
+import torch.distributed as dist
 
 from . import ops
 
@@ -153,6 +155,69 @@ def search_segments(q_repr, input_paths, shard, batch, topk, device="cuda"):
     return ops.topk_merge(torch.cat(all_s, dim=1).contiguous(), torch.cat(all_i, dim=1).contiguous(), topk)
 
 
+# ------------------------------------------------------------------ multi-GPU: index sharded over ranks
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank_files(input_paths, rank, world):
+    """Contiguous block of reps_* files owned by ``rank`` (file order = global row order = passage-file order)."""
+    assert len(input_paths) % world == 0, f"{len(input_paths)} reps_* files do not divide over {world} ranks"
+    per = len(input_paths) // world
+    return input_paths[rank * per:(rank + 1) * per]
+
+
+def global_row_offset(local_rows, device):
+    """Rows held by the lower ranks (one all-gather of a single int64 per rank)."""
+    world = _world()
+    if world == 1:
+        return 0
+    mine = torch.tensor([int(local_rows)], dtype=torch.int64, device=device)
+    every = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(every, mine)
+    return int(sum(int(t.item()) for t in every[:dist.get_rank()]))
+
+
+def gather_rank_lists(scores, indexes):
+    """[Q, k] per rank -> [Q, W * k], rank-major along dim 1: the layout of all_scores / all_indexes in
+    run_retrieval_pytorch.py:218-227 with ranks in place of sequential shards."""
+    world = _world()
+    if world == 1:
+        return scores, indexes
+    ss = [torch.empty_like(scores) for _ in range(world)]
+    ii = [torch.empty_like(indexes) for _ in range(world)]
+    dist.all_gather(ss, scores.contiguous())
+    dist.all_gather(ii, indexes.contiguous())
+    return torch.cat(ss, dim=1).contiguous(), torch.cat(ii, dim=1).contiguous()
+
+
+def search_distributed(q_repr, input_paths, shard, batch, topk, device="cuda"):
+    """Every rank searches its own block of the index (the reps_{rank} files it wrote in generate_embeddings) and
+    the W lists are merged with one all-gather + ops.topk_merge; every rank returns the global result.  The only
+    data-path collective is that all-gather of [Q, k] scores and ids (no corpus bytes move between GPUs)."""
+    world = _world()
+    if world == 1:
+        return search_segments(q_repr, input_paths, shard, batch, topk, device)
+    mine = rank_files(input_paths, dist.get_rank(), world)
+    assert len(mine) % shard == 0, "Invalid Shard number"
+    per = len(mine) // shard
+    all_s, all_i, rows = [], [], 0
+    for seg in range(shard):
+        index = build_index(mine[seg * per:(seg + 1) * per], device)
+        s, i = search_index(q_repr, index, batch, topk, index_offset=rows)     # rank-local row ids for now
+        rows += index.shape[0]
+        del index
+        all_s.append(s)
+        all_i.append(i)
+    s = torch.cat(all_s, dim=1).contiguous()
+    i = torch.cat(all_i, dim=1).contiguous()
+    if shard > 1:
+        s, i = ops.topk_merge(s, i, topk)
+    i = i + global_row_offset(rows, s.device)
+    gs, gi = gather_rank_lists(s, i)
+    return ops.topk_merge(gs, gi, topk)
+
+
 # ------------------------------------------------------------------ output (merge_results :96-137, writer :232-300)
 def merge_results(passages, questions, top_doc_ids, scores_list, trec_format):
     assert len(top_doc_ids) == len(questions) == len(scores_list)
@@ -200,7 +265,12 @@ def main(args, logger=None):
     with open(qpath, "rb") as f:
         q_repr = torch.as_tensor(pickle.load(f))
     print("Retrieving results...")
-    scores, indexes = search_segments(q_repr, input_paths, args.shard, args.batch, args.topk)
+    if "LOCAL_RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1 and not dist.is_initialized():
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+        dist.init_process_group("nccl")
+    scores, indexes = search_distributed(q_repr, input_paths, args.shard, args.batch, args.topk)
+    if _world() > 1 and dist.get_rank() != 0:
+        return                                      # every rank holds the result; rank 0 writes the run file
     if not args.fp32_scores:
         scores = scores.to(torch.float16)
     scores = scores.float().cpu().numpy().astype(np.float64)

@@ -112,3 +112,35 @@ def test_search_full_size_properties():
     s2, i2 = ops.search_topk(q, corpus[h:], k, index_offset=h)
     ms, mi = ops.topk_merge(torch.cat([s1, s2], 1).contiguous(), torch.cat([i1, i2], 1).contiguous(), k)
     assert torch.equal(ms, s) and torch.equal(mi, i)
+
+
+def _dist_worker(rank, world, port, root, ret):
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import glob
+    from dpr_scale_b200 import run_retrieval as RR
+    paths = sorted(glob.glob(os.path.join(root, "emb", "reps_*")))
+    with open(os.path.join(root, "emb", "query_reps.pkl"), "rb") as f:
+        q = pickle.load(f)
+    s, i = RR.search_distributed(q, paths, 1, 100, 10, device=f"cuda:{rank}")
+    s1, i1 = RR.search_segments(q, paths, 1, 100, 10, device=f"cuda:{rank}")        # whole index on one GPU
+    ret[rank] = (bool(torch.equal(s, s1)), bool(torch.equal(i, i1)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_rank_sharded_search_equals_single_gpu(tmp_path):
+    """Index sharded over 2 ranks (NCCL all-gather of the per-rank lists + merge) == one GPU holding the whole index,
+    bit for bit (same fp32 scores, same tie order)."""
+    import torch.multiprocessing as mp
+    _setup(tmp_path, n_files=4, rows=900, d=128, nq=17, seed=5)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_dist_worker, args=(2, 29677, str(tmp_path), ret), nprocs=2, join=True)
+    assert ret[0] == (True, True) and ret[1] == (True, True)

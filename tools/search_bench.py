@@ -69,7 +69,8 @@ def run(N, d, Q, k, iters=10):
     gbs = passes * N * d * 2 / (ms * 1e-3) / 1e9
     print(json.dumps({"N": N, "d": d, "Q": Q, "k": k, "ms": round(ms, 3), "ms_torch_reference_path": round(ms_ref, 3),
                       "speedup": round(ms_ref / ms, 2), "queries_per_s": round(Q / ms * 1e3, 1),
-                      "corpus_stream_GBs": round(gbs, 1), "hbm_peak_GBs": peak, "hbm_frac": round(gbs / peak, 3),
+                      "corpus_stream_GBs": round(gbs, 1) if passes == 1 else None, "hbm_peak_GBs": peak,
+                      "hbm_frac": round(gbs / peak, 3) if passes == 1 else None,   # query tiles share the stream via L2
                       "tflops": round(2.0 * Q * N * d / (ms * 1e-3) / 1e12, 1),
                       "peak_source": src, "fp16_scores_equal": round(same_scores, 5), "ids_equal": round(same_ids, 5)}),
           flush=True)

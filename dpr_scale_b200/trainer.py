@@ -5,6 +5,7 @@ backward / clip / optimizer + scheduler step), ``validate`` / ``test`` loops, on
 gradient all-reduce DDP would do — issued here as NCCL all-reduces over the encoders' FLAT gradient arenas,
 chunked by layer range and overlapped with the remaining backward on a side stream.
 """
+import os
 import time
 import types
 
@@ -23,6 +24,7 @@ class Trainer:
         self.gradient_clip_val = float(gradient_clip_val or 0.0)
         self.world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.global_rank = dist.get_rank() if self.world_size > 1 else 0
+        self.gpus = int(os.environ.get("LOCAL_WORLD_SIZE", self.world_size))   # GPUs of this node (sampler chunking)
         self.strategy = DDPStrategy() if (self.world_size > 1 or strategy in ("ddp", "ddp_sharded")) else None
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.datamodule = None
@@ -41,6 +43,8 @@ class Trainer:
     # ------------------------------------------------------------------ setup
     def attach(self, task, datamodule=None, stage="fit"):
         self.datamodule = datamodule
+        if datamodule is not None and hasattr(datamodule, "trainer"):
+            datamodule.trainer = self
         task.trainer = self
         task.setup(stage)
         task.to(self.device)
@@ -126,6 +130,8 @@ class Trainer:
         task.train()
         done = False
         for epoch in range(self.max_epochs if self.max_epochs and self.max_epochs > 0 else 10 ** 9):
+            if hasattr(datamodule, "set_epoch"):
+                datamodule.set_epoch(epoch)
             for i, batch in enumerate(datamodule.train_dataloader()):
                 if self.limit_train_batches is not None and i >= self.limit_train_batches:
                     break

@@ -14,7 +14,7 @@ import torch.distributed as dist
 import torch.nn as nn
 
 try:  # pragma: no cover - exercised only where Lightning exists
-    from pytorch_lightning import LightningModule  # type: ignore
+    from pytorch_lightning import LightningDataModule, LightningModule  # type: ignore
     from pytorch_lightning.strategies import DDPShardedStrategy, DDPStrategy  # type: ignore
     HAVE_LIGHTNING = True
 except Exception:  # noqa
@@ -25,6 +25,10 @@ except Exception:  # noqa
 
     class DDPShardedStrategy(DDPStrategy):
         pass
+
+    class LightningDataModule:
+        def __init__(self):
+            self.trainer = None
 
     class LightningModule(nn.Module):
         def __init__(self):

@@ -1,0 +1,140 @@
+"""Input pipeline (dpr_scale_b200/datamodule/dpr.py, transforms/) vs golden batches produced by the UNMODIFIED reference
+data code (tests/golden/make_golden_data.py -> data_batches.npz): every batch of every stage, bit for bit, through the
+synchronous loader and through the background-thread loader; line index; distributed sampler orders."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from dpr_scale_b200.datamodule.dpr import (BatchStream, DenseRetrieverJsonlDataModule, LineFile,
+                                           contiguous_shard_indices)
+from dpr_scale_b200.transforms.hf_transform import BertTransform, HFTransform
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DATA = os.path.join(HERE, "golden", "data")
+JSONL = os.path.join(DATA, "synth.jsonl")
+CASES = {
+    "a": dict(batch_size=4, num_negative=3, neg_ctx_sample=True, pos_ctx_sample=False, num_val_negative=2,
+              num_test_negative=5, use_title=True),
+    "b": dict(batch_size=5, num_negative=7, neg_ctx_sample=True, pos_ctx_sample=True, num_val_negative=7,
+              num_test_negative=0, use_title=False, rel_sample=True),
+    "c": dict(batch_size=15, num_negative=0, neg_ctx_sample=False, num_val_negative=1, use_title=False),
+}
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(HERE, "golden", "data_batches.npz"))
+
+
+@pytest.fixture(scope="module")
+def model_dir(tmp_path_factory):
+    from transformers import BertConfig
+    d = tmp_path_factory.mktemp("tok")
+    vocab = open(os.path.join(DATA, "vocab.txt")).read()
+    BertConfig(vocab_size=len(vocab.split()), hidden_size=16, num_hidden_layers=1, num_attention_heads=1,
+               intermediate_size=16).save_pretrained(d)
+    (d / "vocab.txt").write_text(vocab)
+    return str(d)
+
+
+def _same(batch, gold, prefix):
+    for key in ("query_ids", "contexts_ids"):
+        names = [k.split("/")[-1] for k in gold.files if k.startswith(f"{prefix}/{key}/")]
+        assert sorted(names) == sorted(batch[key].keys()), (names, list(batch[key].keys()))
+        for kk in names:
+            got = batch[key][kk]
+            assert got.dtype == torch.int64
+            assert np.array_equal(got.numpy(), gold[f"{prefix}/{key}/{kk}"]), f"{prefix}/{key}/{kk}"
+    assert batch["pos_ctx_indices"].dtype == torch.int64 and batch["scores"].dtype == torch.float32
+    assert batch["ctx_mask"].dtype == torch.bool
+    for key in ("pos_ctx_indices", "scores", "ctx_mask"):
+        assert np.array_equal(batch[key].numpy(), gold[f"{prefix}/{key}"]), f"{prefix}/{key}"
+
+
+@pytest.mark.parametrize("prefetch,fast", [(0, False), (0, True), (3, True)])
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_batches_equal_reference(gold, model_dir, case, prefetch, fast):
+    tf = HFTransform(model_path=model_dir, max_seq_len=24)
+    dm = DenseRetrieverJsonlDataModule(transform=tf, train_path=JSONL, val_path=JSONL, test_path=JSONL,
+                                       prefetch_batches=prefetch, device_prefetch=False, fast_tokenize=fast,
+                                       **CASES[case])
+    np.random.seed(1234)
+    for stage, loader in (("train", dm.train_dataloader()), ("valid", dm.val_dataloader()),
+                          ("test", dm.test_dataloader())):
+        want = int(gold[f"{case}/{stage}/num_batches"])
+        assert len(loader) == want
+        n = 0
+        for i, batch in enumerate(loader):
+            _same(batch, gold, f"{case}/{stage}/{i}")
+            n += 1
+        assert n == want
+
+
+def test_bert_transform_and_pair_inputs(model_dir):
+    t = BertTransform(model_path=model_dir, max_seq_len=8)
+    out = t(["alpha bravo", "charlie delta echo foxtrot golf hotel india juliet"])
+    assert out["input_ids"].shape == (2, 8) and out["attention_mask"][0].sum() == 4     # [CLS] a b [SEP]
+    h = HFTransform(model_path=model_dir, max_seq_len=16, return_tensors=False)
+    pair = h(["alpha"], ["bravo charlie"])
+    assert pair["token_type_ids"][0] == [0, 0, 0, 1, 1, 1]
+
+
+def test_encode_fast_equals_wrapper_call(model_dir):
+    words = open(os.path.join(DATA, "vocab.txt")).read().split()[5:]
+    rnd = np.random.RandomState(0)
+    texts = [" ".join(rnd.choice(words, rnd.randint(0, 40))) for _ in range(200)] + ["", "zzz unknown-word !!"]
+    for max_len in (8, 32):
+        t = HFTransform(model_path=model_dir, max_seq_len=max_len)
+        want, got = t(texts), t.encode_fast(texts)
+        assert list(got.keys()) == list(want.keys())
+        for k in want.keys():
+            assert got[k].dtype == want[k].dtype and torch.equal(got[k], want[k]), k
+    t = HFTransform(model_path=model_dir, max_seq_len=16, add_special_tokens=False)
+    assert torch.equal(t(texts[:50])["input_ids"], t.encode_fast(texts[:50])["input_ids"])
+
+
+def test_line_index(gold, tmp_path):
+    ds = LineFile(JSONL)
+    assert len(ds) == int(gold["n_rows"])
+    assert np.array_equal(np.array([len(ds[i]) for i in range(len(ds))]), gold["lines"])
+    raw = open(JSONL, "rb").read().split(b"\n")
+    assert ds[0] == raw[0] + b"\n" and ds[len(ds) - 1] == raw[-1]          # last line has no newline
+    p = tmp_path / "h.tsv"
+    p.write_text("id\ttext\n1\tx\n2\ty\n")
+    h = LineFile(str(p), header=True)
+    assert len(h) == 2 and h[0] == b"1\tx\n" and h[1] == b"2\ty\n"
+    e = tmp_path / "empty.jsonl"
+    e.write_text("")
+    assert len(LineFile(str(e))) == 0
+    with pytest.raises(KeyError):
+        ds[len(ds)]
+
+
+def test_sampler_orders_equal_reference(gold):
+    n = int(gold["n_rows"])
+    keys = [k for k in gold.files if k.startswith("sampler/")]
+    assert len(keys) == 2 * (2 + 4 + 8 + 3)
+    for k in keys:
+        _, world, per_node, epoch, rank = k.split("/")
+        got = contiguous_shard_indices(n, int(world), int(rank), int(per_node), True, 0, int(epoch), False)
+        assert got == gold[k].tolist(), k
+
+
+def test_stream_propagates_errors_and_stops_early():
+    def bad(rows):
+        if rows[0] == 4:
+            raise ValueError("boom")
+        return {"x": torch.tensor(rows)}
+    s = BatchStream(list(range(10)), lambda: list(range(10)), 2, bad, prefetch_batches=2)
+    it = iter(s)
+    assert next(it)["x"].tolist() == [0, 1] and next(it)["x"].tolist() == [2, 3]
+    with pytest.raises(ValueError):
+        next(it)
+    ok = BatchStream(list(range(100)), lambda: list(range(100)), 10, lambda r: {"x": torch.tensor(r)},
+                     prefetch_batches=2, drop_last=True)
+    for i, b in enumerate(ok):
+        if i == 1:
+            break                        # abandoning the iterator must stop the worker thread
+    assert len(ok) == 10

@@ -10,6 +10,7 @@ A "step" = zero_grad -> both encoders fwd -> (all-gather) -> fused scoring+CE ->
 1 pos + 7 hard negatives (1024 contexts/GPU), in-batch (global when N>1) negatives.  Prints ONE JSON line.
 """
 import argparse
+import contextlib
 import ctypes
 import json
 import math
@@ -320,7 +321,8 @@ def run_b200(args, workload):
         optim={"_target_": "dpr_scale_b200.optim.FusedAdamW", "lr": 1e-5, "betas": [0.9, 0.999], "eps": 1e-8,
                "weight_decay": 0.0})
     trainer = Trainer(max_steps=10 ** 6, gradient_clip_val=2.0, device=dev)
-    trainer.attach(task, None, "fit")
+    with contextlib.redirect_stdout(sys.stderr):      # stdout carries exactly ONE line: the JSON result
+        trainer.attach(task, None, "fit")
     task.train()
     task.context_encoder.activation_chunk = ACT_CHUNK.get(workload, 0)
     host_batch = synth_batch(rank, cfg, B, n, S)

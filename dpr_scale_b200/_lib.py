@@ -93,7 +93,10 @@ def load():
             f"{LIB_PATH} not found: the CUDA extension is not built. Run `python __graft_entry__.py` "
             "(or `make -C dpr_scale_b200/csrc`). There is no CPU fallback."
         )
-    lib = ctypes.CDLL(LIB_PATH)
+    # PyDLL: keep the GIL across the calls.  Every entry point only enqueues kernels (microseconds); releasing and
+    # re-taking the GIL ~10 times per step would make the training thread queue behind the input-pipeline thread
+    # (datamodule/dpr.py) for up to a switch interval each time.
+    lib = ctypes.PyDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         try:
             fn = getattr(lib, name)

@@ -23,6 +23,7 @@ import math
 import mmap
 import os
 import queue
+import sys
 import threading
 
 import numpy as np
@@ -179,6 +180,10 @@ class BatchStream:
                 q.put(("error", e))
 
         worker = threading.Thread(target=produce, name="dprb-batch-stream", daemon=True)
+        # the assembly thread holds the GIL for tens of ms per batch (JSON, Python loops, list -> array); a short
+        # switch interval lets the training thread take it back within 0.5 ms whenever it needs to launch kernels
+        old_interval = sys.getswitchinterval()
+        sys.setswitchinterval(min(old_interval, 5e-4))
         worker.start()
         try:
             while True:
@@ -191,6 +196,7 @@ class BatchStream:
         finally:
             stop.set()
             worker.join(timeout=5.0)
+            sys.setswitchinterval(old_interval)
 
 
 class DenseRetrieverDataModuleBase(LightningDataModule):

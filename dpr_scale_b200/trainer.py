@@ -103,10 +103,6 @@ class Trainer:
                 return True
         return False
 
-    def _unused(self):
-        if True:
-            return
-
     def training_step(self, batch, batch_idx=0):
         """zero_grad -> task.training_step -> backward -> grad all-reduce -> clip + AdamW -> LR schedule."""
         self.optimizer.zero_grad()

@@ -21,7 +21,7 @@ constexpr int FWD_WARPS = 8;
 __global__ void __launch_bounds__(FWD_WARPS * 32)
 score_ce_fwd_kernel(const float* __restrict__ q, const float* __restrict__ c, const uint8_t* __restrict__ col_mask,
                     const uint8_t* __restrict__ pair_mask, const int64_t* __restrict__ labels, float inv_t, float* __restrict__ lse_out,
-                    float* __restrict__ loss_sum, float* __restrict__ logits, int Q, int C, int d) {
+                    float* __restrict__ loss_sum, float* __restrict__ logits, int Q, int C, int d, int cols_per_split) {
   extern __shared__ float sm[];
   float* qs = sm;                       // [QB][d]
   float* red = sm + QB * d;             // [FWD_WARPS][QB][3]
@@ -40,7 +40,9 @@ score_ce_fwd_kernel(const float* __restrict__ q, const float* __restrict__ c, co
 #pragma unroll
   for (int r = 0; r < QB; ++r) { m[r] = -INFINITY; l[r] = 0.f; pick[r] = 0.f; }
 
-  for (int cb = warp * CW; cb < C; cb += FWD_WARPS * CW) {
+  // gridDim.y > 1: this CTA only writes the logits of its column range; score_lse_kernel reduces the rows afterwards
+  const int c_begin = blockIdx.y * cols_per_split, c_end = min(C, c_begin + cols_per_split);
+  for (int cb = c_begin + warp * CW; cb < c_end; cb += FWD_WARPS * CW) {
     float acc[QB][CW];
 #pragma unroll
     for (int r = 0; r < QB; ++r)
@@ -79,6 +81,7 @@ score_ce_fwd_kernel(const float* __restrict__ q, const float* __restrict__ c, co
       }
     }
   }
+  if (gridDim.y > 1) return;
   if (lane == 0) {
 #pragma unroll
     for (int r = 0; r < QB; ++r) {
@@ -108,6 +111,39 @@ score_ce_fwd_kernel(const float* __restrict__ q, const float* __restrict__ c, co
   }
 }
 
+// Row reduction over stored logits (one warp per query row): lse, NLL pick, loss accumulation.
+__global__ void __launch_bounds__(256)
+score_lse_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, float* __restrict__ lse_out,
+                 float* __restrict__ loss_sum, int Q, int C) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  float loss = 0.f;
+  if (r < Q) {
+    const float* row = logits + (long long)r * C;
+    float m = -INFINITY;
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, row[c]);
+    m = warp_max(m);
+    float l = 0.f;
+    if (m != -INFINITY)
+      for (int c = lane; c < C; c += 32) l += __expf(row[c] - m);     // exp(-inf - m) = 0 for masked columns
+    l = warp_sum(l);
+    const float lse = m + logf(l);
+    if (lane == 0) {
+      lse_out[r] = lse;
+      const long long lab = labels[r];
+      loss = lse - ((lab >= 0 && lab < C) ? row[lab] : 0.f);
+    }
+  }
+  __shared__ float part[8];
+  if (lane == 0) part[threadIdx.x >> 5] = loss;
+  __syncthreads();
+  if (threadIdx.x == 0 && loss_sum != nullptr) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += part[w];
+    atomicAdd(loss_sum, t);
+  }
+}
+
 // out[a, k] (+)= sum_b W(a, b) * X[b, k]   with W derived from the stored logits:
 //   W = (exp(logit[r,c] - lse[r]) - [c == label[r]]) * scale
 // MODE 0 (dq): a = query row r in [a0, a0+na), b = all columns c, X = c matrix.
@@ -118,15 +154,18 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
 score_ce_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ lse,
                     const int64_t* __restrict__ labels, const float* __restrict__ X, float scale,
-                    float* __restrict__ out, int Q, int C, int d, int a0, int na) {
+                    float* __restrict__ out, int Q, int C, int d, int a0, int na, int b_per_split) {
   __shared__ float W[BT][AB + 1];
   const int ab = blockIdx.x * AB;           // first local output row
   const int k = blockIdx.y * 256 + threadIdx.x;
-  const int nb = MODE == 0 ? C : Q;
+  const int nb_all = MODE == 0 ? C : Q;
+  // gridDim.z > 1: the reduction range is split over CTAs and the (pre-zeroed) output is accumulated with atomics
+  const int b_begin = blockIdx.z * b_per_split;
+  const int nb = min(nb_all, b_begin + b_per_split);
   float acc[AB];
 #pragma unroll
   for (int i = 0; i < AB; ++i) acc[i] = 0.f;
-  for (int b0 = 0; b0 < nb; b0 += BT) {
+  for (int b0 = b_begin; b0 < nb; b0 += BT) {
     {
       // 256 threads fill the BT x AB weight tile
       int bi, ai;
@@ -160,8 +199,22 @@ score_ce_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ 
   if (k < d) {
 #pragma unroll
     for (int i = 0; i < AB; ++i)
-      if (ab + i < na) out[(long long)(ab + i) * d + k] = acc[i];
+      if (ab + i < na) {
+        if (gridDim.z > 1) atomicAdd(out + (long long)(ab + i) * d + k, acc[i]);
+        else out[(long long)(ab + i) * d + k] = acc[i];
+      }
   }
+}
+
+int sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
 }
 
 }  // namespace
@@ -179,9 +232,26 @@ int score_ce_fwd(const float* q, const float* c, const uint8_t* col_mask, const 
     DPRB_CHECK_CUDA(cudaFuncSetAttribute(score_ce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
-  score_ce_fwd_kernel<<<(Q + QB - 1) / QB, FWD_WARPS * 32, smem, stream>>>(q, c, col_mask, pair_mask, labels, inv_t, lse,
-                                                                           loss_sum, logits, Q, C, d);
+  // With the logits stored anyway (training), spread the columns over ~4 CTAs per SM and reduce the rows in a second
+  // small kernel: at Q x C = 1024 x 8192 (8 GPUs) the one-CTA-per-8-rows form took ms, not us.
+  const int row_blocks = (Q + QB - 1) / QB;
+  const int step = FWD_WARPS * CW;
+  int splits = 1;
+  if (logits != nullptr) {
+    splits = (4 * sm_count() + row_blocks - 1) / row_blocks;
+    const int max_splits = (C + step - 1) / step;
+    splits = splits < 1 ? 1 : (splits > max_splits ? max_splits : splits);
+  }
+  const int cols_per_split = ((C + splits - 1) / splits + step - 1) / step * step;
+  splits = (C + cols_per_split - 1) / cols_per_split;
+  dim3 grid(row_blocks, splits);
+  score_ce_fwd_kernel<<<grid, FWD_WARPS * 32, smem, stream>>>(q, c, col_mask, pair_mask, labels, inv_t, lse, loss_sum,
+                                                              logits, Q, C, d, cols_per_split);
   DPRB_CHECK_CUDA(cudaGetLastError());
+  if (splits > 1) {
+    score_lse_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(logits, labels, lse, loss_sum, Q, C);
+    DPRB_CHECK_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 
@@ -193,16 +263,24 @@ int score_ce_bwd(const float* q, const float* c, const float* logits, const int6
                "score_ce_bwd: local ranges out of bounds (q0=%d nq=%d c0=%d nc=%d)", q0, nq, c0, nc);
   DPRB_REQUIRE(logits != nullptr && lse != nullptr, "score_ce_bwd: logits and lse from forward required");
   const float scale = grad_scale * inv_t / (float)Q;  // d(mean CE)/d(logit) * d(logit)/d(q.c)
-  if (nq > 0 && dq != nullptr) {
-    dim3 grid((nq + AB - 1) / AB, (d + 255) / 256);
-    score_ce_bwd_kernel<0><<<grid, 256, 0, stream>>>(logits, lse, labels, c, scale, dq, Q, C, d, q0, nq);
+  // split the reduction dimension until there are ~2 CTAs per SM (dq at 8 GPUs: 16 x 3 CTAs reducing 8192 columns)
+  auto launch = [&](auto kern, const float* X, float* out, int a0, int na, int nb) -> int {
+    const int base = ((na + AB - 1) / AB) * ((d + 255) / 256);
+    int z = (2 * sm_count() + base - 1) / base;
+    const int max_z = (nb + 4 * BT - 1) / (4 * BT);
+    z = z < 1 ? 1 : (z > max_z ? max_z : z);
+    const int per = ((nb + z - 1) / z + BT - 1) / BT * BT;
+    z = (nb + per - 1) / per;
+    if (z > 1) DPRB_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)na * d * sizeof(float), stream));
+    dim3 grid((na + AB - 1) / AB, (d + 255) / 256, z);
+    kern<<<grid, 256, 0, stream>>>(logits, lse, labels, X, scale, out, Q, C, d, a0, na, per);
     DPRB_CHECK_CUDA(cudaGetLastError());
-  }
-  if (nc > 0 && dc != nullptr) {
-    dim3 grid((nc + AB - 1) / AB, (d + 255) / 256);
-    score_ce_bwd_kernel<1><<<grid, 256, 0, stream>>>(logits, lse, labels, q, scale, dc, Q, C, d, c0, nc);
-    DPRB_CHECK_CUDA(cudaGetLastError());
-  }
+    return 0;
+  };
+  if (nq > 0 && dq != nullptr)
+    if (int rc = launch(score_ce_bwd_kernel<0>, c, dq, q0, nq, C)) return rc;
+  if (nc > 0 && dc != nullptr)
+    if (int rc = launch(score_ce_bwd_kernel<1>, q, dc, c0, nc, Q)) return rc;
   return 0;
 }
 

@@ -286,6 +286,10 @@ CHECKS = {
 }
 
 # tcgen05 attention (S <= 128) extra shapes: many problems (persistent loop, barrier phases), heads=12
+CHECKS["score_ce_8gpu_shape"] = lambda: check_score_ce(Q=1024, C=8192, d=768, inv_t=0.125, q0=256, nq=128, c0=2048,
+                                                       nc=1024, seed=16)     # cfg 3: global 1024 x 8192 scores per rank
+CHECKS["score_ce_ragged_splits"] = lambda: check_score_ce(Q=70, C=1999, d=200, inv_t=0.5, q0=3, nq=60, c0=17, nc=1500,
+                                                          seed=17)
 CHECKS["attn_tc_many"] = lambda: check_attention(40, 128, 12, True, seed=9)
 CHECKS["attn_tc_s64_many"] = lambda: check_attention(33, 64, 4, True, seed=10)
 CHECKS["attn_tc_s37"] = lambda: check_attention(5, 37, 2, True, seed=11)

@@ -19,6 +19,7 @@ parse, negative sampling, tokenise ~(2+n)·B sequences, then a blocking H2D copy
 
 ``prefetch_batches=0`` gives the plain synchronous loader (used by the parity tests to compare batch for batch).
 """
+import ast
 import math
 import mmap
 import os
@@ -29,7 +30,7 @@ import threading
 import numpy as np
 import torch
 
-from ..transforms.dpr_transform import DPRTransform
+from ..transforms.dpr_transform import DPRTransform, maybe_add_title
 from ..transforms.hf_transform import HFTransform
 from ..utils.lightning_shim import LightningDataModule
 
@@ -66,10 +67,68 @@ class LineFile:
     def __getitem__(self, index):
         if not 0 <= index < self.count:
             raise KeyError(index)
+        index = int(index)                  # retrieval hands over float row ids (np.zeros result arrays)
         return self.process_line(bytes(self.mm[self._bounds[index]:self._bounds[index + 1]]))
+
+    def __iter__(self):
+        return (self[i] for i in range(self.count))
 
 
 MemoryMappedDataset = LineFile   # the reference's name
+
+
+def _split_quoted(line, sep):
+    """One delimited row with the reference's minimal csv unquoting (datamodule/dpr.py:94-100)."""
+    row = line.decode().rstrip("\r\n").split(sep)
+    return [v.strip('"').replace('""', '"') if v and v[0] == '"' and v[-1] == '"' else v for v in row]
+
+
+class CSVDataset(LineFile):
+    """Delimited file with a header row -> dict per row (datamodule/dpr.py:80-107).  A row whose field count differs
+    from the header yields None, as in the reference (its fallback evaluates row 0 but does not return it)."""
+
+    def __init__(self, path, sep="\t"):
+        super().__init__(path, header=False)
+        self.sep = sep
+        self.columns = _split_quoted(bytes(self.mm[self._bounds[0]:self._bounds[1]]), sep) if self.count else []
+        self._bounds = self._bounds[1:]
+        self.count = max(self.count - 1, 0)
+
+    def process_line(self, line):
+        vals = _split_quoted(line, self.sep)
+        if len(self.columns) == len(vals):
+            return dict(zip(self.columns, vals))
+        return None
+
+
+class QueryCSVDataset(LineFile):
+    """question <sep> python-literal list of answers, no header (datamodule/dpr.py:110-134)."""
+
+    def __init__(self, path, sep="\t"):
+        super().__init__(path, header=False)
+        self.sep = sep
+
+    def process_line(self, line):
+        vals = _split_quoted(line, self.sep)
+        return {"question": vals[0], "answers": ast.literal_eval(vals[1])}
+
+
+class QueryTSVDataset(LineFile):
+    """qid <sep> question, no header (datamodule/dpr.py:137-159)."""
+
+    def __init__(self, path, sep="\t"):
+        super().__init__(path, header=False)
+        self.sep = sep
+
+    def process_line(self, line):
+        vals = _split_quoted(line, self.sep)
+        return {"id": vals[0], "question": vals[1]}
+
+
+def contiguous_test_shard(n, num_replicas, rank):
+    """Row range of ``ContiguousDistributedSamplerForTest`` (utils/utils.py:83-91): contiguous, unpadded."""
+    shard = n // num_replicas + 1
+    return list(range(rank * shard, min((rank + 1) * shard, n)))
 
 
 def contiguous_shard_indices(n, num_replicas, rank, replicas_per_node=1, shuffle=True, seed=0, epoch=0,
@@ -290,3 +349,68 @@ class DenseRetrieverJsonlDataModule(DenseRetrieverDataModuleBase):
             return self.dpr_transform(batch, stage)
         rows = batch if type(batch) is list else batch[self.dpr_transform.text_column]
         return self.dpr_transform.finish(self.dpr_transform.select(rows, stage))
+
+
+class _EncodeOnlyDataModule(DenseRetrieverDataModuleBase):
+    """Shared loader logic of the two embedding-generation datamodules (datamodule/dpr.py:457-479, :507-529): one
+    'test' split, every loader is the test loader, contiguous unpadded shards across ranks."""
+
+    def _encode(self, texts):
+        tf = self.text_transform
+        if self.fast_tokenize and hasattr(tf, "encode_fast"):
+            return tf.encode_fast(texts)
+        return self._transform(texts)
+
+    def _test_order(self):
+        n = len(self.datasets["test"])
+        tr = getattr(self, "trainer", None)
+        world = getattr(tr, "world_size", 1) if tr is not None else 1
+        if world and world > 1:
+            return contiguous_test_shard(n, world, tr.global_rank)
+        return list(range(n))
+
+    def test_dataloader(self):
+        return self._stream("test", self._test_order, self.test_batch_size, self.collate_test)
+
+    def val_dataloader(self):
+        return self.test_dataloader()
+
+    def train_dataloader(self):
+        return self.test_dataloader()
+
+
+class DenseRetrieverPassagesDataModule(_EncodeOnlyDataModule):
+    """Passage TSV (id, text, title) for generate_embeddings (datamodule/dpr.py:415-479)."""
+
+    def __init__(self, transform, test_path: str, test_batch_size: int = 128, num_workers: int = 0,
+                 use_title: bool = False, sep_token: str = " [SEP] ", prefetch_batches: int = 4,
+                 device_prefetch: bool = True, fast_tokenize: bool = True, *args, **kwargs):
+        super().__init__(transform)
+        self.test_batch_size = test_batch_size
+        self.use_title = use_title
+        self.sep_token = sep_token
+        self.num_workers = num_workers
+        self.prefetch_batches, self.device_prefetch, self.fast_tokenize = prefetch_batches, device_prefetch, fast_tokenize
+        self.datasets = {"test": CSVDataset(test_path)}
+
+    def collate(self, batch, stage):
+        ctx = self._encode([maybe_add_title(row["text"], row["title"], self.use_title, self.sep_token) for row in batch])
+        if "id" in batch[0]:
+            return {"contexts_ids": ctx, "corpus_ids": [row["id"] for row in batch]}
+        return {"contexts_ids": ctx}
+
+
+class DenseRetrieverQueriesDataModule(_EncodeOnlyDataModule):
+    """Question file for generate_query_embeddings (datamodule/dpr.py:482-529)."""
+
+    def __init__(self, transform, test_path: str, test_batch_size: int = 128, num_workers: int = 0,
+                 trec_format: bool = False, prefetch_batches: int = 4, device_prefetch: bool = True,
+                 fast_tokenize: bool = True, *args, **kwargs):
+        super().__init__(transform)
+        self.test_batch_size = test_batch_size
+        self.num_workers = num_workers
+        self.prefetch_batches, self.device_prefetch, self.fast_tokenize = prefetch_batches, device_prefetch, fast_tokenize
+        self.datasets = {"test": QueryTSVDataset(test_path) if trec_format else QueryCSVDataset(test_path)}
+
+    def collate(self, batch, stage):
+        return {"query_ids": self._encode([row["question"] for row in batch])}

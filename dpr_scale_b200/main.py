@@ -21,7 +21,7 @@ def main(argv=None):
     cfg = compose(name, argv)
     cfg.task.datamodule = None
     task = instantiate(cfg.task, _recursive_=False)
-    assert cfg.task.model.model_path == cfg.task.transform.text_transform.model_path
+    assert cfg.task.model.model_path == cfg.task.transform.model_path
     transform = instantiate(cfg.task.transform)
     datamodule = instantiate(cfg.datamodule, transform=transform)
     tr_kw = {k: v for k, v in cfg.trainer.items() if k in ("max_steps", "max_epochs", "gradient_clip_val", "precision",

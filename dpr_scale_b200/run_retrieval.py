@@ -16,7 +16,6 @@ Under torchrun the index is sharded over the ranks (each GPU searches the reps_*
 [Q, k] lists; merge) - see search_distributed.  There is no CPU path: without the CUDA library the ops raise DprbError.
 """
 import argparse
-import ast
 import glob
 import json
 import logging
@@ -29,6 +28,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
+from .datamodule.dpr import CSVDataset, QueryCSVDataset, QueryTSVDataset
 
 
 def get_logger():
@@ -52,71 +52,17 @@ def get_parser():
     p.add_argument("--ignore_identical_ids", action="store_true",
                    help="this is used for BEIR Arguana and Quora datasets")
     p.add_argument("--fp32_scores", action="store_true", help="write fp32 scores instead of fp16-rounded ones")
+    p.add_argument("--device", type=str, default="cuda", help="device holding the index (the kernels need CUDA)")
     return p
 
 
 # ------------------------------------------------------------------ tab-separated inputs (datamodule/dpr.py:80-159)
-def _unquote(line, sep="\t"):
-    row = line.rstrip("\r\n").split(sep)
-    return [v.strip('"').replace('""', '"') if v and v[0] == '"' and v[-1] == '"' else v for v in row]
+Passages = CSVDataset            # id / text / title table with a header row
 
 
-class TableFile:
-    """Random access to the rows of a tab-separated file through a byte-offset table (rows stay on disk)."""
-
-    def __init__(self, path, header):
-        self.path = path
-        self._f = open(path, "rb")
-        offsets, pos = [], 0
-        for line in self._f:
-            offsets.append(pos)
-            pos += len(line)
-        self.columns = None
-        if header and offsets:
-            self.columns = self.row(offsets[0])
-            offsets = offsets[1:]
-        self._offsets = offsets
-
-    def row(self, offset):
-        self._f.seek(offset)
-        return _unquote(self._f.readline().decode())
-
-    def __len__(self):
-        return len(self._offsets)
-
-    def __getitem__(self, i):
-        return self.parse(self.row(self._offsets[int(i)]))
-
-    def __iter__(self):
-        return (self[i] for i in range(len(self)))
-
-    def parse(self, vals):
-        return vals
-
-
-class Passages(TableFile):
-    """id / text / title table with a header row (CSVDataset, datamodule/dpr.py:80-107)."""
-
-    def __init__(self, path):
-        super().__init__(path, header=True)
-
-    def parse(self, vals):
-        if len(vals) != len(self.columns):
-            return self[0]                       # the reference falls back to row 0 on malformed lines
-        return dict(zip(self.columns, vals))
-
-
-class Questions(TableFile):
-    """question \\t answers (QueryCSVDataset :110-134) or, for trec, qid \\t question (QueryTSVDataset :137-159)."""
-
-    def __init__(self, path, trec_format):
-        super().__init__(path, header=False)
-        self.trec_format = trec_format
-
-    def parse(self, vals):
-        if self.trec_format:
-            return {"id": vals[0], "question": vals[1]}
-        return {"question": vals[0], "answers": ast.literal_eval(vals[1])}
+def Questions(path, trec_format):
+    """question \\t answers (QueryCSVDataset) or, for trec, qid \\t question (QueryTSVDataset)."""
+    return QueryTSVDataset(path) if trec_format else QueryCSVDataset(path)
 
 
 # ------------------------------------------------------------------ search
@@ -268,7 +214,7 @@ def main(args, logger=None):
     if "LOCAL_RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1 and not dist.is_initialized():
         torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
         dist.init_process_group("nccl")
-    scores, indexes = search_distributed(q_repr, input_paths, args.shard, args.batch, args.topk)
+    scores, indexes = search_distributed(q_repr, input_paths, args.shard, args.batch, args.topk, args.device)
     if _world() > 1 and dist.get_rank() != 0:
         return                                      # every rank holds the result; rank 0 writes the run file
     if not args.fp32_scores:

@@ -61,6 +61,22 @@ def write_inputs():
         for row in rows[:-1]:
             f.write(json.dumps(row) + "\n")
         f.write(json.dumps(rows[-1]))            # last line without newline
+    # passage table (generate_embeddings input) with csv quoting and one malformed row, question files (both formats)
+    with open(os.path.join(DATA, "passages.tsv"), "w") as f:
+        f.write("id\ttext\ttitle\n")
+        for i in range(11):
+            t = text(3, 30)
+            if i == 3:
+                t = '"' + t + ' ""quoted"" tail"'
+            f.write(f"{i + 1}\t{t}\t{text(1, 3)}\n")
+    with open(os.path.join(DATA, "malformed.tsv"), "w") as f:
+        f.write("id\ttext\ttitle\n1\tfine text\tfine title\nbroken row without tabs\n")
+    with open(os.path.join(DATA, "questions.csv"), "w") as f:
+        for i in range(7):
+            f.write(f"{text(2, 9)}\t{[text(1, 2), text(1, 1)]!r}\n")
+    with open(os.path.join(DATA, "questions.tsv"), "w") as f:
+        for i in range(7):
+            f.write(f"q{i}\t{text(2, 9)}\n")
     return len(rows)
 
 
@@ -127,6 +143,32 @@ def main():
                     dump(out, f"{name}/{stage}/{i}", batch)
                     nb += 1
                 out[f"{name}/{stage}/num_batches"] = nb
+        from dpr_scale.datamodule.dpr import (CSVDataset, DenseRetrieverPassagesDataModule,
+                                              DenseRetrieverQueriesDataModule)
+        from dpr_scale.utils.utils import ContiguousDistributedSamplerForTest
+        pdm = {"t": DenseRetrieverPassagesDataModule(tf, os.path.join(DATA, "passages.tsv"), test_batch_size=5, use_title=True),
+               "n": DenseRetrieverPassagesDataModule(tf, os.path.join(DATA, "passages.tsv"), test_batch_size=12)}
+        for name, dm in pdm.items():
+            for i, batch in enumerate(dm.test_dataloader()):
+                for kk in batch["contexts_ids"].keys():
+                    out[f"passages/{name}/{i}/{kk}"] = batch["contexts_ids"][kk].numpy()
+                out[f"passages/{name}/{i}/corpus_ids"] = np.array(batch["corpus_ids"])
+            out[f"passages/{name}/num_batches"] = i + 1
+        for name, fn, trec in (("csv", "questions.csv", False), ("tsv", "questions.tsv", True)):
+            dm = DenseRetrieverQueriesDataModule(tf, os.path.join(DATA, fn), test_batch_size=3, trec_format=trec)
+            for i, batch in enumerate(dm.test_dataloader()):
+                for kk in batch["query_ids"].keys():
+                    out[f"queries/{name}/{i}/{kk}"] = batch["query_ids"][kk].numpy()
+            out[f"queries/{name}/num_batches"] = i + 1
+        csv = CSVDataset(os.path.join(DATA, "passages.tsv"))
+        out["csv_len"] = len(csv)
+        out["csv_row3_text"] = np.array(csv[3]["text"])
+        bad = CSVDataset(os.path.join(DATA, "malformed.tsv"))
+        out["csv_malformed_is_none"] = np.array(bad[1] is None)      # dpr.py:102-107 evaluates row 0 and returns None
+        for world in (2, 3, 8):
+            for rank in range(world):
+                smp = ContiguousDistributedSamplerForTest(csv, num_replicas=world, rank=rank)
+                out[f"test_sampler/{world}/{rank}"] = np.array(list(iter(smp)), dtype=np.int64)
         ds = MemoryMappedDataset(path)
         out["lines"] = np.array([len(ds[i]) for i in range(len(ds))])
         # sampler orders: (world, rank, replicas_per_node, epoch)

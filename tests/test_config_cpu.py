@@ -14,7 +14,7 @@ def test_compose_defaults_and_overrides():
     assert cfg.task._target_ == "dpr_scale_b200.task.dpr_task.DenseRetrieverTask"
     assert cfg.task.model._target_ == "dpr_scale_b200.models.hf_model.HFEncoder"
     assert cfg.task.model.model_path == "/tmp/m"
-    assert cfg.task.transform.text_transform.model_path == "/tmp/m"  # ${task.model.model_path} interpolation
+    assert cfg.task.transform.model_path == "/tmp/m"  # ${task.model.model_path} interpolation
     assert cfg.task.warmup_steps == 7 and cfg.task.k == 3
     assert cfg.task.optim.lr == 2.0e-05 and cfg.task.optim._target_.endswith("FusedAdamW")
     assert cfg.trainer.gradient_clip_val == 2.0 and cfg.datamodule.num_negative == 7
@@ -74,3 +74,42 @@ def test_state_dict_roundtrip_keeps_arena_views():
     assert k_off - q_off == 128 * 128
     w = b.transformer.encoder.layer._modules["0"].attention.self.query.weight
     assert w.data_ptr() == b.master.data_ptr() + 4 * q_off
+
+
+def test_generation_tasks_host_logic(tmp_path):
+    """Writers of the two embedding-generation tasks on CPU tensors (no encoder involved): file names, pickle protocol 4
+    of ONE fp32 tensor, default query path = <ctx_embeddings_dir>/query_reps.pkl (dpr_eval_task.py:36-49, :52-84)."""
+    import pickle
+
+    import torch
+
+    from dpr_scale_b200.task.dpr_eval_task import GenerateEmbeddingsTask, GenerateQueryEmbeddingsTask
+    kw = dict(transform={}, model={}, datamodule=None, optim={})
+    t = GenerateEmbeddingsTask(ctx_embeddings_dir=str(tmp_path / "emb"), checkpoint_path="", **kw)
+    parts = [torch.arange(6, dtype=torch.float32).view(2, 3) + 10 * i for i in range(3)]
+    path = t.test_epoch_end([t._to_pinned(p) for p in parts])
+    assert path.endswith("emb/reps_0000.pkl")
+    raw = open(path, "rb").read()
+    assert raw[:2] == b"\x80\x04"                                  # pickle protocol 4
+    assert torch.equal(pickle.loads(raw), torch.cat(parts))
+    q = GenerateQueryEmbeddingsTask(ctx_embeddings_dir=str(tmp_path / "emb"), checkpoint_path="", **kw)
+    assert q.query_emb_output_path == str(tmp_path / "emb" / "query_reps.pkl")
+    out = q.test_epoch_end(parts)
+    assert torch.equal(pickle.load(open(out, "rb")), torch.cat(parts))
+    q2 = GenerateQueryEmbeddingsTask(ctx_embeddings_dir=str(tmp_path / "emb"), checkpoint_path="",
+                                     query_emb_output_path=str(tmp_path / "x" / "q.pkl"), **kw)
+    assert q2.test_epoch_end(parts) == str(tmp_path / "x" / "q.pkl")
+
+
+def test_generation_configs_compose():
+    from dpr_scale_b200.utils.config import compose
+    cfg = compose("config", ["datamodule=generate", "datamodule.test_path=/tmp/p.tsv", "task.model.model_path=/m",
+                             "+task.ctx_embeddings_dir=/out"])
+    assert cfg.datamodule._target_.endswith("DenseRetrieverPassagesDataModule") and cfg.datamodule.use_title is True
+    assert cfg.datamodule.test_path == "/tmp/p.tsv" and cfg.task.ctx_embeddings_dir == "/out"
+    assert "train_path" not in cfg.datamodule
+    cfg = compose("config", ["datamodule=generate_query_emb", "datamodule.test_path=/tmp/q.tsv",
+                             "+datamodule.trec_format=true"])
+    assert cfg.datamodule._target_.endswith("DenseRetrieverQueriesDataModule") and cfg.datamodule.trec_format is True
+    assert cfg.task.transform._target_ == "dpr_scale_b200.transforms.hf_transform.HFTransform"
+    assert cfg.task.transform.model_path == cfg.task.model.model_path

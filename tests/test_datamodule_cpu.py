@@ -138,3 +138,66 @@ def test_stream_propagates_errors_and_stops_early():
         if i == 1:
             break                        # abandoning the iterator must stop the worker thread
     assert len(ok) == 10
+
+
+# ------------------------------------------------------------------ embedding-generation datamodules (generate*.yaml)
+@pytest.mark.parametrize("prefetch,fast", [(0, False), (2, True)])
+def test_passages_datamodule_equals_reference(gold, model_dir, prefetch, fast):
+    from dpr_scale_b200.datamodule.dpr import DenseRetrieverPassagesDataModule
+    tf = HFTransform(model_path=model_dir, max_seq_len=24)
+    path = os.path.join(DATA, "passages.tsv")
+    for name, kw in (("t", dict(test_batch_size=5, use_title=True)), ("n", dict(test_batch_size=12))):
+        dm = DenseRetrieverPassagesDataModule(tf, path, prefetch_batches=prefetch, device_prefetch=False,
+                                              fast_tokenize=fast, **kw)
+        n = 0
+        for i, batch in enumerate(dm.test_dataloader()):
+            for kk, v in batch["contexts_ids"].items():
+                assert np.array_equal(v.numpy(), gold[f"passages/{name}/{i}/{kk}"]), (name, i, kk)
+            assert batch["corpus_ids"] == gold[f"passages/{name}/{i}/corpus_ids"].tolist()
+            n += 1
+        assert n == int(gold[f"passages/{name}/num_batches"]) == len(dm.val_dataloader()) == len(dm.train_dataloader())
+
+
+def test_queries_datamodule_equals_reference(gold, model_dir):
+    from dpr_scale_b200.datamodule.dpr import DenseRetrieverQueriesDataModule
+    tf = HFTransform(model_path=model_dir, max_seq_len=24)
+    for name, fn, trec in (("csv", "questions.csv", False), ("tsv", "questions.tsv", True)):
+        dm = DenseRetrieverQueriesDataModule(tf, os.path.join(DATA, fn), test_batch_size=3, trec_format=trec,
+                                             device_prefetch=False)
+        n = 0
+        for i, batch in enumerate(dm.test_dataloader()):
+            assert list(batch.keys()) == ["query_ids"]
+            for kk, v in batch["query_ids"].items():
+                assert np.array_equal(v.numpy(), gold[f"queries/{name}/{i}/{kk}"]), (name, i, kk)
+            n += 1
+        assert n == int(gold[f"queries/{name}/num_batches"])
+
+
+def test_csv_dataset_and_test_sampler(gold):
+    from dpr_scale_b200.datamodule.dpr import CSVDataset, QueryCSVDataset, contiguous_test_shard
+    csv = CSVDataset(os.path.join(DATA, "passages.tsv"))
+    assert len(csv) == int(gold["csv_len"]) and csv.columns == ["id", "text", "title"]
+    assert csv[3]["text"] == str(gold["csv_row3_text"]) and '"quoted" tail' in csv[3]["text"]
+    assert csv[np.float64(2.0)]["id"] == "3"
+    bad = CSVDataset(os.path.join(DATA, "malformed.tsv"))
+    assert bool(gold["csv_malformed_is_none"]) and bad[1] is None and bad[0]["id"] == "1"
+    q = QueryCSVDataset(os.path.join(DATA, "questions.csv"))
+    assert isinstance(q[0]["answers"], list) and len(q[0]["answers"]) == 2
+    for k in [k for k in gold.files if k.startswith("test_sampler/")]:
+        _, world, rank = k.split("/")
+        assert contiguous_test_shard(len(csv), int(world), int(rank)) == gold[k].tolist(), k
+
+
+def test_rank_shards_of_passages_datamodule(model_dir):
+    """With a multi-rank trainer every rank loads its contiguous, unpadded slice (dpr.py:463-470)."""
+    import types
+
+    from dpr_scale_b200.datamodule.dpr import DenseRetrieverPassagesDataModule
+    tf = HFTransform(model_path=model_dir, max_seq_len=24)
+    seen = []
+    for rank in range(3):
+        dm = DenseRetrieverPassagesDataModule(tf, os.path.join(DATA, "passages.tsv"), test_batch_size=2,
+                                              device_prefetch=False)
+        dm.trainer = types.SimpleNamespace(world_size=3, global_rank=rank)
+        seen.append([i for b in dm.test_dataloader() for i in b["corpus_ids"]])
+    assert seen == [["1", "2", "3", "4"], ["5", "6", "7", "8"], ["9", "10", "11"]]

@@ -60,3 +60,47 @@ def test_parser_matches_reference_flags():
     assert (a.topk, a.batch, a.shard, a.run_name, a.trec_format, a.ignore_identical_ids) == (100, 100, 1, "dpr", False, False)
     for flag in ("ctx_embeddings_dir", "query_emb_path", "questions_tsv_path", "passages_tsv_path", "output_runfile_path"):
         assert getattr(a, flag) == ""
+
+
+def test_main_flow_with_emulated_search(tmp_path, monkeypatch):
+    """Whole script flow (reps_* pickles -> segments -> merge -> run file) on the CPU with the two kernels replaced by
+    torch emulations - host logic only; the kernels themselves are checked on the GPU (tests/test_retrieval_gpu.py)."""
+    import pickle
+
+    import torch
+
+    from dpr_scale_b200 import ops
+
+    def fake_search(q, c, k, index_offset=0):
+        s = q.float() @ c.float().T
+        v, i = torch.sort(s, dim=1, descending=True, stable=True)
+        return v[:, :k].contiguous(), i[:, :k] + index_offset
+
+    def fake_merge(s, idx, k):
+        v, o = torch.sort(s, dim=1, descending=True, stable=True)
+        return v[:, :k].contiguous(), torch.gather(idx, 1, o[:, :k])
+    monkeypatch.setattr(ops, "search_topk", fake_search)
+    monkeypatch.setattr(ops, "topk_merge", fake_merge)
+    g = torch.Generator().manual_seed(0)
+    emb = tmp_path / "emb"
+    emb.mkdir()
+    shards = [torch.randn(40, 16, generator=g) for _ in range(4)]
+    for r, t in enumerate(shards):
+        pickle.dump(t, open(emb / f"reps_{r:04}.pkl", "wb"), protocol=4)
+    q = torch.randn(3, 16, generator=g)
+    pickle.dump(q, open(emb / "query_reps.pkl", "wb"), protocol=4)
+    with open(tmp_path / "p.tsv", "w") as f:
+        f.write("id\ttext\ttitle\n" + "".join(f"p{i}\ttext {i}\ttitle {i}\n" for i in range(160)))
+    with open(tmp_path / "q.tsv", "w") as f:
+        f.write("".join(f"q{i}\tquestion {i}\n" for i in range(3)))
+    full = torch.cat(shards).half().float()
+    want = torch.sort(q.half().float() @ full.T, dim=1, descending=True, stable=True)[1][:, :5]
+    for shard in (1, 2, 4):
+        out = tmp_path / f"run{shard}.trec"
+        RR.main(RR.get_parser().parse_args([
+            "--ctx_embeddings_dir", str(emb), "--questions_tsv_path", str(tmp_path / "q.tsv"), "--passages_tsv_path",
+            str(tmp_path / "p.tsv"), "--output_runfile_path", str(out), "--topk", "5", "--shard", str(shard),
+            "--trec_format", "--device", "cpu"]))
+        rows = [l.split() for l in open(out).read().splitlines()]
+        assert [r[2] for r in rows] == [f"p{int(j)}" for j in want.flatten()], shard
+        assert [int(r[3]) for r in rows] == [1, 2, 3, 4, 5] * 3

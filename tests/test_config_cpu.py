@@ -113,3 +113,44 @@ def test_generation_configs_compose():
     assert cfg.datamodule._target_.endswith("DenseRetrieverQueriesDataModule") and cfg.datamodule.trec_format is True
     assert cfg.task.transform._target_ == "dpr_scale_b200.transforms.hf_transform.HFTransform"
     assert cfg.task.transform.model_path == cfg.task.model.model_path
+
+
+def test_generation_scripts_wire_task_transform_and_datamodule(tmp_path, monkeypatch):
+    """generate_embeddings / generate_query_embeddings up to the trainer call: config composition with the reference's
+    override syntax, `_target_` swap, transform and datamodule instantiation (the encoder itself needs a GPU)."""
+    from transformers import BertConfig
+
+    from dpr_scale_b200 import generate_embeddings as GE
+    from dpr_scale_b200 import generate_query_embeddings as GQ
+    model = tmp_path / "model"
+    model.mkdir()
+    BertConfig(vocab_size=12, hidden_size=16, num_hidden_layers=1, num_attention_heads=1,
+               intermediate_size=16).save_pretrained(model)
+    (model / "vocab.txt").write_text("\n".join(["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]", "a", "b", "c", "d", "e", "f", "g"]) + "\n")
+    (tmp_path / "p.tsv").write_text("id\ttext\ttitle\n" + "".join(f"{i}\ta b c\td e\n" for i in range(5)))
+    (tmp_path / "q.tsv").write_text("".join(f"q{i}\tf g a\n" for i in range(3)))
+    seen = {}
+
+    class StubTrainer:
+        def __init__(self, **kw):
+            pass
+
+        def test(self, task, datamodule):
+            seen["task"] = type(task).__name__
+            seen["dm"] = type(datamodule).__name__
+            datamodule.device_prefetch = False
+            seen["batches"] = [b for b in datamodule.test_dataloader()]
+            seen["out"] = getattr(task, "query_emb_output_path", None) or task.ctx_embeddings_dir
+            return seen
+    monkeypatch.setattr(GE, "Trainer", StubTrainer)
+    common = [f"task.model.model_path={model}", f"+task.ctx_embeddings_dir={tmp_path / 'emb'}", "+task.checkpoint_path="]
+    GE.main(["-m", "--config-name", "msmarco_baseline.yaml", "datamodule=generate",
+             f"datamodule.test_path={tmp_path / 'p.tsv'}", "datamodule.test_batch_size=2"] + common)
+    assert seen["task"] == "GenerateEmbeddingsTask" and seen["dm"] == "DenseRetrieverPassagesDataModule"
+    assert len(seen["batches"]) == 3 and seen["batches"][0]["corpus_ids"] == ["0", "1"]
+    assert seen["batches"][0]["contexts_ids"]["input_ids"][0].tolist() == [2, 8, 9, 3, 5, 6, 7, 3]   # [CLS] d e [SEP] a b c [SEP]
+    GQ.main(["datamodule=generate_query_emb", f"datamodule.test_path={tmp_path / 'q.tsv'}", "+datamodule.trec_format=true"]
+            + common)
+    assert seen["task"] == "GenerateQueryEmbeddingsTask" and seen["dm"] == "DenseRetrieverQueriesDataModule"
+    assert seen["out"] == str(tmp_path / "emb" / "query_reps.pkl")
+    assert seen["batches"][0]["query_ids"]["input_ids"].tolist() == [[2, 10, 11, 5, 3]] * 3

@@ -13,7 +13,6 @@ import argparse
 import contextlib
 import ctypes
 import json
-import math
 import os
 import subprocess
 import sys

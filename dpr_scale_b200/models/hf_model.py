@@ -15,7 +15,6 @@ import ctypes
 import json
 import math
 import os
-import warnings
 from typing import Mapping, Optional
 
 import torch

@@ -6,8 +6,6 @@ gradient all-reduce DDP would do — issued here as NCCL all-reduces over the en
 chunked by layer range and overlapped with the remaining backward on a side stream.
 """
 import os
-import time
-import types
 
 import torch
 import torch.distributed as dist

@@ -12,7 +12,6 @@ Parameter names are the HF state_dict names (prefix ``transformer.`` as in HFEnc
 import math
 
 import torch
-import torch.nn.functional as F
 
 
 def roberta_position_ids(input_ids, pad_id):

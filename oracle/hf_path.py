@@ -4,7 +4,6 @@
 (b) as the timed CPU baseline of bench.py (``cpu_baseline`` and ``--impl reference``).
 transformers is a dependency of the reference (requirements.txt:6, pinned 3.4.0; 5.5.0 installed here).
 """
-import torch
 import torch.nn as nn
 
 

@@ -16,7 +16,6 @@ import sys
 import types
 
 import numpy as np
-import torch
 
 REF = "/root/reference"
 HERE = os.path.dirname(os.path.abspath(__file__))

@@ -20,7 +20,7 @@ def _worker(rank, world, port, ret):
     from dpr_scale_b200.task.dpr_task import DenseRetrieverTask
     from dpr_scale_b200.trainer import Trainer
     from tests.test_task_gpu import CFG, _batch
-    from tests.util import load_golden, rel_l2, sub
+    from tests.util import load_golden, sub
     g2, g1 = load_golden("golden_2rank.npz"), load_golden("golden_1rank.npz")
     task = DenseRetrieverTask(transform={}, datamodule=None, shared_model=False, softmax_temperature=float(g1["temperature"]),
                               model={"_target_": "dpr_scale_b200.models.hf_model.HFEncoder.from_config", "config": CFG, "dropout": 0.0},

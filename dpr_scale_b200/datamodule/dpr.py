@@ -24,6 +24,7 @@ import math
 import mmap
 import os
 import queue
+import random
 import sys
 import threading
 
@@ -75,6 +76,22 @@ class LineFile:
 
 
 MemoryMappedDataset = LineFile   # the reference's name
+
+
+class MultiSourceDataset:
+    """Several JSONL files of (at least) ``min`` rows: row i is read from a file drawn with ``random.choice`` at every
+    access (datamodule/dpr.py:56-77); the draw order is part of the behaviour, so accesses stay sequential."""
+
+    def __init__(self, paths, header=False):
+        self.datasets = [LineFile(path, header) for path in paths]
+        self.data_size = min(len(d) for d in self.datasets)
+        assert self.data_size > 0, "One of the path in datamodule.train_path is empty"
+
+    def __len__(self):
+        return self.data_size
+
+    def __getitem__(self, index):
+        return random.choice(self.datasets)[index]
 
 
 def _split_quoted(line, sep):
@@ -349,6 +366,20 @@ class DenseRetrieverJsonlDataModule(DenseRetrieverDataModuleBase):
             return self.dpr_transform(batch, stage)
         rows = batch if type(batch) is list else batch[self.dpr_transform.text_column]
         return self.dpr_transform.finish(self.dpr_transform.select(rows, stage))
+
+
+class DenseRetrieverMultiJsonlDataModule(DenseRetrieverJsonlDataModule):
+    """Several training files sampled per row + contexts given as ``docidx`` into a corpus table
+    (datamodule/dpr.py:333-412, the DRAGON configs): the JSONL rows stay light and DPRTransform reads text / title of
+    the selected contexts from the mmap'ed corpus."""
+
+    def __init__(self, transform, train_path, val_path: str, test_path: str, corpus_path: str = None, *args, **kwargs):
+        first = train_path[0] if not isinstance(train_path, str) else train_path
+        super().__init__(transform, first, val_path, test_path, *args, **kwargs)
+        paths = [train_path] if isinstance(train_path, str) else list(train_path)
+        self.datasets["train"] = MultiSourceDataset(paths)
+        if corpus_path is not None:
+            self.dpr_transform.corpus = LineFile(corpus_path, header=True)
 
 
 class _EncodeOnlyDataModule(DenseRetrieverDataModuleBase):

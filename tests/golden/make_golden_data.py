@@ -68,6 +68,18 @@ def write_inputs():
             if i == 3:
                 t = '"' + t + ' ""quoted"" tail"'
             f.write(f"{i + 1}\t{t}\t{text(1, 3)}\n")
+    # DRAGON-style inputs: corpus table + two light training files that reference it by docidx
+    with open(os.path.join(DATA, "corpus.tsv"), "w") as f:
+        f.write("id\ttext\ttitle\n")
+        for i in range(40):
+            f.write(f"d{i}\t{text(3, 20)}\t{text(1, 3)}\n")
+    for name, nrows in (("light_a.jsonl", 9), ("light_b.jsonl", 7)):
+        with open(os.path.join(DATA, name), "w") as f:
+            for r in range(nrows):
+                f.write(json.dumps({"query_id": str(r), "question": text(2, 10),
+                                    "positive_ctxs": [{"docidx": rnd.randrange(40), "score": str(rnd.random())}
+                                                      for _ in range(1 + r % 2)],
+                                    "hard_negative_ctxs": [{"docidx": rnd.randrange(40)} for _ in range(r % 4)]}) + "\n")
     with open(os.path.join(DATA, "malformed.tsv"), "w") as f:
         f.write("id\ttext\ttitle\n1\tfine text\tfine title\nbroken row without tabs\n")
     with open(os.path.join(DATA, "questions.csv"), "w") as f:
@@ -168,6 +180,20 @@ def main():
             for rank in range(world):
                 smp = ContiguousDistributedSamplerForTest(csv, num_replicas=world, rank=rank)
                 out[f"test_sampler/{world}/{rank}"] = np.array(list(iter(smp)), dtype=np.int64)
+        from dpr_scale.datamodule.dpr import DenseRetrieverMultiJsonlDataModule
+        la, lb = os.path.join(DATA, "light_a.jsonl"), os.path.join(DATA, "light_b.jsonl")
+        mdm = DenseRetrieverMultiJsonlDataModule(transform=tf, train_path=[la, lb], val_path=la, test_path=lb,
+                                                 corpus_path=os.path.join(DATA, "corpus.tsv"), batch_size=3, num_negative=2,
+                                                 pos_ctx_sample=True, num_val_negative=1, num_test_negative=3, use_title=True)
+        random.seed(5)
+        np.random.seed(99)
+        for stage, loader in (("train", mdm.train_dataloader()), ("valid", mdm.val_dataloader()),
+                              ("test", mdm.test_dataloader())):
+            nb = 0
+            for i, batch in enumerate(loader):
+                dump(out, f"multi/{stage}/{i}", batch)
+                nb += 1
+            out[f"multi/{stage}/num_batches"] = nb
         ds = MemoryMappedDataset(path)
         out["lines"] = np.array([len(ds[i]) for i in range(len(ds))])
         # sampler orders: (world, rank, replicas_per_node, epoch)

@@ -201,3 +201,27 @@ def test_rank_shards_of_passages_datamodule(model_dir):
         dm.trainer = types.SimpleNamespace(world_size=3, global_rank=rank)
         seen.append([i for b in dm.test_dataloader() for i in b["corpus_ids"]])
     assert seen == [["1", "2", "3", "4"], ["5", "6", "7", "8"], ["9", "10", "11"]]
+
+
+@pytest.mark.parametrize("prefetch", [0, 2])
+def test_multi_jsonl_corpus_datamodule_equals_reference(gold, model_dir, prefetch):
+    """DRAGON-style input (dragon_aws.yaml): several training files drawn per row with random.choice, contexts fetched
+    from a corpus table by docidx (datamodule/dpr.py:333-412)."""
+    import random
+
+    from dpr_scale_b200.datamodule.dpr import DenseRetrieverMultiJsonlDataModule
+    tf = HFTransform(model_path=model_dir, max_seq_len=24)
+    la, lb = os.path.join(DATA, "light_a.jsonl"), os.path.join(DATA, "light_b.jsonl")
+    dm = DenseRetrieverMultiJsonlDataModule(transform=tf, train_path=[la, lb], val_path=la, test_path=lb,
+                                            corpus_path=os.path.join(DATA, "corpus.tsv"), batch_size=3, num_negative=2,
+                                            pos_ctx_sample=True, num_val_negative=1, num_test_negative=3, use_title=True,
+                                            prefetch_batches=prefetch, device_prefetch=False)
+    assert len(dm.datasets["train"]) == 7
+    random.seed(5)
+    np.random.seed(99)
+    for stage, loader in (("train", dm.train_dataloader()), ("valid", dm.val_dataloader()), ("test", dm.test_dataloader())):
+        n = 0
+        for i, batch in enumerate(loader):
+            _same(batch, gold, f"multi/{stage}/{i}")
+            n += 1
+        assert n == int(gold[f"multi/{stage}/num_batches"])

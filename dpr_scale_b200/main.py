@@ -25,13 +25,17 @@ def main(argv=None):
     transform = instantiate(cfg.task.transform)
     datamodule = instantiate(cfg.datamodule, transform=transform)
     tr_kw = {k: v for k, v in cfg.trainer.items() if k in ("max_steps", "max_epochs", "gradient_clip_val", "precision",
-                                                             "strategy", "log_every_n_steps")}
-    trainer = Trainer(**tr_kw)
+                                                             "strategy", "log_every_n_steps", "limit_train_batches",
+                                                             "limit_val_batches", "check_val_every_n_epoch")}
+    checkpoint_callback = instantiate(cfg.checkpoint_callback) if cfg.get("checkpoint_callback") else None
+    trainer = Trainer(callbacks=[checkpoint_callback] if checkpoint_callback is not None else [], **tr_kw)
     if cfg.test_only:
-        trainer.test(task, datamodule)
+        trainer.test(task, datamodule, ckpt_path=cfg.task.get("pretrained_checkpoint_path"))
     else:
         trainer.fit(task, datamodule)
-        trainer.test(task, datamodule)
+        if checkpoint_callback is not None:
+            print(f"*** Best model path is {checkpoint_callback.best_model_path}")
+        trainer.test(task, datamodule, ckpt_path="best")
 
 
 if __name__ == "__main__":

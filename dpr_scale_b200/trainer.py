@@ -16,7 +16,7 @@ from .utils.lightning_shim import DDPStrategy
 class Trainer:
     def __init__(self, max_steps=-1, max_epochs=1, gradient_clip_val=0.0, strategy=None, precision=16,
                  log_every_n_steps=50, limit_train_batches=None, limit_val_batches=None, device=None,
-                 grad_bucket_layers=3, **unused):
+                 grad_bucket_layers=3, callbacks=None, check_val_every_n_epoch=1, **unused):
         self.max_steps = max_steps
         self.max_epochs = max_epochs
         self.gradient_clip_val = float(gradient_clip_val or 0.0)
@@ -34,6 +34,9 @@ class Trainer:
         self.limit_train_batches = limit_train_batches
         self.limit_val_batches = limit_val_batches
         self.weights_save_path = "."
+        self.callbacks = list(callbacks or [])
+        self.check_val_every_n_epoch = int(check_val_every_n_epoch or 0)
+        self.current_epoch = 0
 
     def set_grad_compression(self, on):
         self.compress_grads = bool(on)
@@ -135,9 +138,24 @@ class Trainer:
                 if self.max_steps and 0 < self.max_steps <= self.global_step:
                     done = True
                     break
+            self._end_of_epoch(task, datamodule, epoch)
             if done:
                 break
         return task
+
+    def _end_of_epoch(self, task, datamodule, epoch):
+        """What Lightning does between epochs for this path: a validation pass, then the checkpoint callbacks
+        (main.py:30-32 registers ModelCheckpoint monitoring valid_mrr)."""
+        self.current_epoch = epoch
+        metrics = None
+        has_val = datamodule is not None and hasattr(datamodule, "val_dataloader")
+        if has_val and self.check_val_every_n_epoch > 0 and (epoch + 1) % self.check_val_every_n_epoch == 0:
+            metrics = self.validate(task, datamodule)
+        for cb in self.callbacks:
+            if hasattr(cb, "on_validation_end"):
+                cb.on_validation_end(task, epoch, self.global_step, metrics, is_writer=self.global_rank == 0)
+        if self.world_size > 1:
+            dist.barrier()
 
     @torch.no_grad()
     def _eval_loop(self, task, loader, step_name, end_name, limit=None):
@@ -155,8 +173,16 @@ class Trainer:
         dm = datamodule or self.datamodule
         return self._eval_loop(task, dm.val_dataloader(), "validation_step", "validation_epoch_end", self.limit_val_batches)
 
-    def test(self, task, datamodule=None, ckpt_path=None):
+    def test(self, task=None, datamodule=None, ckpt_path=None, **unused):
+        task = task if task is not None else self.task
         dm = datamodule or self.datamodule
         if getattr(task, "trainer", None) is None:
             self.attach(task, dm, "test")
+        if ckpt_path:                                   # "best" = the checkpoint callback's choice (main.py:46-47)
+            from .utils.checkpoint import load_into
+            if ckpt_path == "best":
+                ckpt_path = next((cb.best_model_path for cb in self.callbacks if getattr(cb, "best_model_path", "")), "")
+            if ckpt_path:
+                load_into(task, ckpt_path)
+                task.to(self.device)
         return self._eval_loop(task, dm.test_dataloader(), "test_step", "test_epoch_end")

@@ -54,3 +54,78 @@ def test_min_mode_missing_metric_and_non_writer_rank(tmp_path):
     other = ModelCheckpoint(dirpath=str(tmp_path / "b"), monitor=None, save_top_k=1, save_last=True)
     other.on_validation_end(m, 0, 5, None, is_writer=False)                 # ranks != 0 track paths but write nothing
     assert other.best_model_path.endswith("epoch=0-step=5.ckpt") and not os.path.exists(tmp_path / "b")
+
+
+class StubTask(torch.nn.Module):
+    """Lightning-hook-shaped stand-in (no encoders): lets the trainer's loop logic run on the CPU."""
+
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.tensor([4.0]))
+        self.trainer = None
+        self.setup_done = False
+        self.val_calls = 0
+
+    def setup(self, stage):
+        self.setup_done = True
+
+    def configure_optimizers(self):
+        opt = torch.optim.SGD(self.parameters(), lr=0.25)
+        return [opt], [{"scheduler": torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 1.0), "interval": "step"}]
+
+    def training_step(self, batch, idx):
+        return (self.w * batch["x"]).pow(2).sum()
+
+    def validation_step(self, batch, idx):
+        return float(batch["x"].sum())
+
+    def validation_epoch_end(self, outs):
+        self.val_calls += 1
+        return {"valid_mrr": torch.tensor(1.0 / (1.0 + abs(float(self.w)))), "n": len(outs)}
+
+    def test_step(self, batch, idx):
+        return float(self.w)
+
+    def test_epoch_end(self, outs):
+        return {"w_seen": outs[0], "n": len(outs)}
+
+
+class StubData:
+    trainer = None
+
+    def __init__(self):
+        self.epochs = []
+
+    def set_epoch(self, e):
+        self.epochs.append(e)
+
+    def train_dataloader(self):
+        return [{"x": torch.tensor([1.0])} for _ in range(3)]
+
+    def val_dataloader(self):
+        return [{"x": torch.tensor([1.0])} for _ in range(2)]
+
+    test_dataloader = val_dataloader
+
+
+def test_fit_validates_checkpoints_and_tests_best(tmp_path):
+    from dpr_scale_b200.trainer import Trainer
+    cb = ModelCheckpoint(dirpath=str(tmp_path), monitor="valid_mrr", mode="max", save_last=True, save_top_k=1,
+                         filename="checkpoint_best")
+    task, data = StubTask(), StubData()
+    tr = Trainer(max_epochs=3, device="cpu", callbacks=[cb], log_every_n_steps=1000)
+    tr.fit(task, data)
+    assert data.epochs == [0, 1, 2] and task.val_calls == 3 and tr.global_step == 9 and data.trainer is tr
+    assert abs(float(task.w)) < 4.0                              # SGD on w^2 shrinks |w| every step
+    files = sorted(os.listdir(tmp_path))                           # best = last epoch (smallest |w|); older ones pruned
+    assert len(files) == 2 and files[0].startswith("checkpoint_best") and files[1] == "last.ckpt"
+    best_w = float(torch.load(cb.best_model_path, weights_only=False)["state_dict"]["w"])
+    assert abs(best_w - float(task.w)) < 1e-7
+    with torch.no_grad():
+        task.w.fill_(123.0)
+    res = tr.test(None, data, ckpt_path="best")                  # main.py:46-47: test the best checkpoint
+    assert abs(res["w_seen"] - best_w) < 1e-7 and res["n"] == 2
+    tr2 = Trainer(max_epochs=5, max_steps=4, device="cpu", check_val_every_n_epoch=0)
+    t2 = StubTask()
+    tr2.fit(t2, StubData())
+    assert tr2.global_step == 4 and t2.val_calls == 0

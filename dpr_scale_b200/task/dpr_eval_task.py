@@ -1,9 +1,11 @@
-"""GenerateEmbeddingsTask — mirror of ``dpr_scale.task.dpr_eval_task.GenerateEmbeddingsTask``
-(/root/reference/dpr_scale/task/dpr_eval_task.py:13-49): forward-only context encoding of a contiguous corpus shard,
-written as ``reps_{rank:04}.pkl`` (pickle protocol 4 of one fp32 tensor, byte-compatible with the reference's output).
+"""Forward-only embedding dumps: ``GenerateEmbeddingsTask`` (passages -> ``reps_{rank:04}.pkl``) and
+``GenerateQueryEmbeddingsTask`` (questions -> ``query_reps.pkl``), drop-ins for the classes of the same names in
+/root/reference/dpr_scale/task/dpr_eval_task.py (:13-49 and :52-84): same constructor keywords, same Lightning test
+hooks, same output files (pickle protocol 4 of ONE fp32 CPU tensor, which is what run_retrieval reads).
 
-Differences that matter on a B200: the encoder runs in ``save_for_backward=0`` mode (two activation slots instead
-of L), results are copied to a pinned host buffer asynchronously (no per-batch ``.cpu()`` sync) and concatenated once.
+How a B200 changes the loop: the encoder runs in its forward-only mode (two activation slots instead of one per layer),
+every batch result goes to a pinned host buffer with an asynchronous copy instead of the reference's blocking ``.cpu()``
+per batch, and the device is synchronised once, right before the shard is concatenated and written.
 """
 import os
 import pathlib
@@ -15,60 +17,83 @@ import torch.distributed as dist
 from .dpr_task import DenseRetrieverTask
 
 
-class GenerateEmbeddingsTask(DenseRetrieverTask):
-    def __init__(self, ctx_embeddings_dir, checkpoint_path, **kwargs):
-        super().__init__(**kwargs)
+class _EmbeddingDumpTask(DenseRetrieverTask):
+    """Shared machinery: which batch entry to encode, with which encoder, and where the shard goes."""
+
+    batch_key = None
+
+    def __init__(self, ctx_embeddings_dir, checkpoint_path, **task_kwargs):
+        super().__init__(**task_kwargs)
         self.ctx_embeddings_dir = ctx_embeddings_dir
         self.checkpoint_path = checkpoint_path
         pathlib.Path(ctx_embeddings_dir).mkdir(parents=True, exist_ok=True)
 
     def setup(self, stage: str):
-        super().setup("train")
-        if self.checkpoint_path:
-            print(f"Loading checkpoint from {self.checkpoint_path}")
-            ckpt = torch.load(self.checkpoint_path, map_location="cpu", weights_only=False)
-            self.load_state_dict(ckpt["state_dict"])
+        super().setup("train")                       # always build the encoders, whatever stage the trainer names
+        if not self.checkpoint_path:
+            return
+        print(f"Loading checkpoint from {self.checkpoint_path}")
+        state = torch.load(self.checkpoint_path, map_location="cpu", weights_only=False)["state_dict"]
+        self.load_state_dict(state)
 
-    def forward(self, contexts_ids):
-        return self.encode_contexts(contexts_ids)
+    # -- per-batch: encode, then park the result in pinned memory without waiting for it
+    def _encode(self, tokens):
+        raise NotImplementedError
+
+    def forward(self, tokens):
+        return self._encode(tokens)
 
     @staticmethod
     def _to_pinned(rep):
-        """Asynchronous D2H into a pinned buffer (the reference syncs with ``.cpu()`` every batch, :35)."""
-        host = torch.empty(rep.shape, dtype=rep.dtype, pin_memory=rep.is_cuda)
-        host.copy_(rep, non_blocking=True)
-        return host
+        parked = torch.empty(rep.shape, dtype=rep.dtype, pin_memory=rep.is_cuda)
+        parked.copy_(rep, non_blocking=True)
+        return parked
 
+    @torch.no_grad()
+    def _eval_step(self, batch, batch_idx):
+        return self._to_pinned(self(batch[self.batch_key]))
+
+    def test_step(self, batch, batch_idx):
+        return self._eval_step(batch, batch_idx)
+
+    # -- per-shard: one sync, one concatenation, one pickle
     @staticmethod
     def _collect(parts):
         if torch.cuda.is_available():
             torch.cuda.synchronize()
         return torch.cat(parts, dim=0)
 
-    @torch.no_grad()
-    def _eval_step(self, batch, batch_idx):
-        return self._to_pinned(self(batch["contexts_ids"]))
+    @staticmethod
+    def _dump(tensor, out_file):
+        pathlib.Path(out_file).parent.mkdir(parents=True, exist_ok=True)
+        print(f"\nWriting tensor of size {tensor.size()} to {out_file}")
+        with open(out_file, mode="wb") as f:
+            pickle.dump(tensor, f, protocol=4)
+        return out_file
 
-    def test_step(self, batch, batch_idx):
-        return self._eval_step(batch, batch_idx)
+
+class GenerateEmbeddingsTask(_EmbeddingDumpTask):
+    """Passage side: context encoder over ``batch["contexts_ids"]``; every rank writes its own shard file."""
+
+    batch_key = "contexts_ids"
+
+    def _encode(self, contexts_ids):
+        return self.encode_contexts(contexts_ids)
 
     def test_epoch_end(self, contexts_repr):
-        contexts_repr = self._collect(contexts_repr)
+        shard = self._collect(contexts_repr)
         if not self.ctx_embeddings_dir:
             self.ctx_embeddings_dir = getattr(self.trainer, "weights_save_path", ".")
-        out_file = os.path.join(self.ctx_embeddings_dir, f"reps_{self.global_rank:04}.pkl")
-        print(f"\nWriting tensor of size {contexts_repr.size()} to {out_file}")
-        with open(out_file, mode="wb") as f:
-            pickle.dump(contexts_repr, f, protocol=4)
+        out_file = self._dump(shard, os.path.join(self.ctx_embeddings_dir, f"reps_{self.global_rank:04}.pkl"))
         if dist.is_available() and dist.is_initialized():
-            dist.barrier()
+            dist.barrier()                           # nobody leaves before every shard is on disk (:49)
         return out_file
 
 
 class GenerateQueryEmbeddingsTask(GenerateEmbeddingsTask):
-    """Mirror of ``GenerateQueryEmbeddingsTask`` (/root/reference/dpr_scale/task/dpr_eval_task.py:52-84): encode the
-    question file with the query encoder and write one fp32 tensor to ``query_emb_output_path`` (default
-    ``<ctx_embeddings_dir>/query_reps.pkl``, the file run_retrieval reads)."""
+    """Question side: query encoder over ``batch["query_ids"]``; one file, by default next to the passage shards."""
+
+    batch_key = "query_ids"
 
     def __init__(self, hnsw_index=False, output_path="/tmp/results.jsonl", query_emb_output_path=None, passages="",
                  **kwargs):
@@ -77,18 +102,8 @@ class GenerateQueryEmbeddingsTask(GenerateEmbeddingsTask):
         self.output_path = output_path
         self.query_emb_output_path = query_emb_output_path or os.path.join(self.ctx_embeddings_dir, "query_reps.pkl")
 
-    def forward(self, query_ids):
+    def _encode(self, query_ids):
         return self.encode_queries(query_ids)
 
-    @torch.no_grad()
-    def _eval_step(self, batch, batch_idx):
-        return self._to_pinned(self(batch["query_ids"]))
-
     def test_epoch_end(self, queries_repr):
-        queries_repr = self._collect(queries_repr)
-        out_file = self.query_emb_output_path
-        pathlib.Path(out_file).parent.mkdir(parents=True, exist_ok=True)
-        print(f"\nWriting tensor of size {queries_repr.size()} to {out_file}")
-        with open(out_file, mode="wb") as f:
-            pickle.dump(queries_repr, f, protocol=4)
-        return out_file
+        return self._dump(self._collect(queries_repr), self.query_emb_output_path)

@@ -154,3 +154,23 @@ def test_generation_scripts_wire_task_transform_and_datamodule(tmp_path, monkeyp
     assert seen["task"] == "GenerateQueryEmbeddingsTask" and seen["dm"] == "DenseRetrieverQueriesDataModule"
     assert seen["out"] == str(tmp_path / "emb" / "query_reps.pkl")
     assert seen["batches"][0]["query_ids"]["input_ids"].tolist() == [[2, 10, 11, 5, 3]] * 3
+
+
+def test_committed_bench_line_has_the_contract_keys():
+    """The bench line recorded in profiles/ (a real B200 run of `python bench.py`) carries every key of the bench
+    contract, with consistent values - guards the schema against accidental edits of bench.py's output dict."""
+    import json
+    line = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_default_line.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in line, k
+    assert line["unit"] == "pairs/s" and line["higher_is_better"] is True and line["scaling"] == "weak"
+    assert line["config"]["workload"] == "bert-base_s128_b128_n7" and line["n_gpus"] == 1
+    assert abs(line["value"] - 128 / (line["ms_per_step"] / 1e3)) < 1e-6 * line["value"]
+    e2e = line["e2e"]
+    assert e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0 and e2e["value"] != line["value"]
+    rf = line["roofline"]
+    assert rf["bound"] == "tensor" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and rf["unit"] == "TFLOP/s"
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] > 0
+    assert line["gpu_launches"] > 0 and set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}

@@ -237,23 +237,26 @@ class BatchStream:
         q = queue.Queue(maxsize=self.prefetch_batches)
         stop = threading.Event()
 
+        def offer(msg):
+            """Blocking put that gives up as soon as the consumer has gone away."""
+            while not stop.is_set():
+                try:
+                    q.put(msg, timeout=0.1)
+                    return True
+                except queue.Full:
+                    continue
+            return False
+
         def produce():
             try:
                 if copy_stream is not None:
                     torch.cuda.set_device(self.device)
                 for b in self._batches():
-                    item = self._stage(b, copy_stream)
-                    while not stop.is_set():
-                        try:
-                            q.put(("batch", item), timeout=0.1)
-                            break
-                        except queue.Full:
-                            continue
-                    if stop.is_set():
+                    if not offer(("batch", self._stage(b, copy_stream))):
                         return
-                q.put(("end", None))
+                offer(("end", None))
             except BaseException as e:  # noqa: surfaced on the training thread
-                q.put(("error", e))
+                offer(("error", e))
 
         worker = threading.Thread(target=produce, name="dprb-batch-stream", daemon=True)
         # the assembly thread holds the GIL for tens of ms per batch (JSON, Python loops, list -> array); a short

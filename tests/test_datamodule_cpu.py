@@ -225,3 +225,16 @@ def test_multi_jsonl_corpus_datamodule_equals_reference(gold, model_dir, prefetc
             _same(batch, gold, f"multi/{stage}/{i}")
             n += 1
         assert n == int(gold[f"multi/{stage}/num_batches"])
+
+
+def test_stream_worker_exits_promptly_when_abandoned_with_full_queue():
+    """Consumer stops after one batch while the producer has finished everything and sits on a full queue: closing
+    the iterator must not wait for the join timeout."""
+    import time
+    s = BatchStream(list(range(6)), lambda: list(range(6)), 1, lambda r: {"x": torch.tensor(r)}, prefetch_batches=2)
+    it = iter(s)
+    next(it)
+    time.sleep(0.5)                       # producer: queue full, remaining batches / "end" pending
+    t0 = time.perf_counter()
+    it.close()
+    assert time.perf_counter() - t0 < 2.0

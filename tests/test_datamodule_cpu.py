@@ -238,3 +238,27 @@ def test_stream_worker_exits_promptly_when_abandoned_with_full_queue():
     t0 = time.perf_counter()
     it.close()
     assert time.perf_counter() - t0 < 2.0
+
+
+def test_line_index_matches_readlines_on_random_files(tmp_path):
+    """LineFile == file.readlines() (what the reference's readline loop yields) on random byte soups: empty lines,
+    CRLF, unicode, with and without a trailing newline, spanning several scan windows."""
+    import dpr_scale_b200.datamodule.dpr as D
+    rng = np.random.RandomState(3)
+    alphabet = ["a", "b", " ", "\t", "\r", "é", "漢", '"', "\n", "\n"]
+    old = D._SCAN_BYTES
+    D._SCAN_BYTES = 37                                     # force many scan windows
+    try:
+        for trial in range(40):
+            text = "".join(rng.choice(alphabet, size=rng.randint(0, 400)))
+            p = tmp_path / f"f{trial}.txt"
+            p.write_bytes(text.encode())
+            want = open(p, "rb").readlines()
+            ds = LineFile(str(p))
+            assert len(ds) == len(want), (trial, text)
+            assert [ds[i] for i in range(len(ds))] == want, trial
+            if want:
+                hdr = LineFile(str(p), header=True)
+                assert [hdr[i] for i in range(len(hdr))] == want[1:], trial
+    finally:
+        D._SCAN_BYTES = old

@@ -49,6 +49,7 @@ SIGNATURES = {
     "dprb_version": (c_int, []),
     "dprb_last_error": (c_char_p, []),
     "dprb_num_sms": (c_int, []),
+    "dprb_launch_count": (c_int64, []),
     "dprb_gemm_bf16": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_int, c_int,
                                _P, _P, c_int64, _P, c_float, c_int, _P, c_float, c_uint64, _P]),
     "dprb_gemm_profile_enable": (c_int, [c_int, c_int]),
@@ -71,6 +72,7 @@ SIGNATURES = {
     "dprb_adamw_step": (c_int, [_P, _P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int,
                                 c_float, _P, c_float, _P]),
     "dprb_cast_f32_bf16": (c_int, [_P, _P, c_int64, _P]),
+    "dprb_cast_bf16_f32": (c_int, [_P, _P, c_int64, _P]),
     "dprb_encoder_workspace_bytes": (c_int64, [POINTER(EncoderWeights), c_int, c_int, c_int]),
     "dprb_encoder_fwd": (c_int, [POINTER(EncoderWeights), POINTER(EncoderBatch), _P, _P]),
     "dprb_encoder_bwd": (c_int, [POINTER(EncoderWeights), POINTER(EncoderBatch), _P, c_int, c_int, _P]),

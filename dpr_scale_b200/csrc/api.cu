@@ -1,5 +1,6 @@
 // C-ABI surface of libdprb.so (declared in include/dprb.h): thin extern "C" shims over the C++
 // launchers, plus the thread-local error string.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include "common.cuh"
@@ -15,6 +16,9 @@ void set_last_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int num_sms() {
   static int cached = 0;
@@ -37,6 +41,7 @@ extern "C" {
 int dprb_version(void) { return DPRB_VERSION; }
 const char* dprb_last_error(void) { return g_err; }
 int dprb_num_sms(void) { return num_sms(); }
+int64_t dprb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int dprb_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int64_t lda, int64_t ldb,
                    int64_t ldd, int a_mn_major, int b_mn_major, int epilogue, const float* bias, const void* aux,
@@ -120,6 +125,9 @@ int dprb_adamw_step(float* p, const float* g, float* m, float* v, void* shadow, 
 }
 int dprb_cast_f32_bf16(const float* src, void* dst, int64_t n, dprb_stream_t stream) {
   return cast_f32_bf16(src, dst, n, S(stream));
+}
+int dprb_cast_bf16_f32(const void* src, float* dst, int64_t n, dprb_stream_t stream) {
+  return cast_bf16_f32(src, dst, n, S(stream));
 }
 int64_t dprb_encoder_workspace_bytes(const dprb_encoder_weights* w, int nseq, int Sq, int save) {
   return encoder_workspace_bytes(w, nseq, Sq, save);

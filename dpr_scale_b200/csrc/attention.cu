@@ -390,7 +390,7 @@ int attn_fwd_lse(const void* qkv, const int32_t* attn_mask, void* ctx, float* ls
   }
   dim3 grid(heads, nseq);
   attn_fwd_kernel<<<grid, 256, smem, stream>>>((const bf16*)qkv, attn_mask, (bf16*)ctx, lse, S, S_pad, heads);
-  DPRB_CHECK_CUDA(cudaGetLastError());
+  DPRB_LAUNCH_CHECK();
   return 0;
 }
 
@@ -418,7 +418,7 @@ int attn_bwd_lse(const void* qkv, const int32_t* attn_mask, const void* ctx, con
   dim3 grid(heads, nseq);
   attn_bwd_kernel<<<grid, 256, smem, stream>>>((const bf16*)qkv, attn_mask, (const bf16*)ctx, lse, (const bf16*)dctx,
                                               (bf16*)dqkv, S, S_pad, heads);
-  DPRB_CHECK_CUDA(cudaGetLastError());
+  DPRB_LAUNCH_CHECK();
   // legacy (mma.sync) path: the QKV bias gradient is a separate streaming pass
   if (dbias != nullptr) return colsum_bf16(dqkv, 3LL * heads * DH, dbias, nseq * S, 3 * heads * DH, stream);
   return 0;

@@ -518,7 +518,7 @@ int attn_fwd_tc(const void* qkv, const int32_t* attn_mask, void* ctx, float* lse
   const int grid = nprob < 2 * sms ? nprob : 2 * sms;  // two co-resident CTAs per SM interleave their serial chains
   if (drop.on()) attn_fwd_tc_kernel<true><<<grid, NTHREADS, FWD_SMEM, stream>>>(tq, tc, attn_mask, lse, S, heads, nseq, drop);
   else attn_fwd_tc_kernel<false><<<grid, NTHREADS, FWD_SMEM, stream>>>(tq, tc, attn_mask, lse, S, heads, nseq, drop);
-  DPRB_CHECK_CUDA(cudaGetLastError());
+  DPRB_LAUNCH_CHECK();
   return 0;
 }
 
@@ -543,7 +543,7 @@ int attn_bwd_tc(const void* qkv, const int32_t* attn_mask, const float* lse, con
   const int grid = nprob < sms ? nprob : sms;
   if (drop.on()) attn_bwd_tc_kernel<true><<<grid, BWD_THREADS, BWD_SMEM, stream>>>(tq, tdo, tdq, attn_mask, lse, dbias, S, heads, nseq, drop);
   else attn_bwd_tc_kernel<false><<<grid, BWD_THREADS, BWD_SMEM, stream>>>(tq, tdo, tdq, attn_mask, lse, dbias, S, heads, nseq, drop);
-  DPRB_CHECK_CUDA(cudaGetLastError());
+  DPRB_LAUNCH_CHECK();
   return 0;
 }
 

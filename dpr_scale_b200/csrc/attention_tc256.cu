@@ -527,7 +527,7 @@ int attn_fwd_tc2(const void* qkv, const int32_t* attn_mask, void* ctx, float* ls
   const int grid = nprob < sms ? nprob : sms;
   if (drop.on()) attn_fwd_tc2_kernel<true><<<grid, F2_THREADS, F2_SMEM, stream>>>(tq, tc, attn_mask, lse, S, heads, nseq, drop);
   else attn_fwd_tc2_kernel<false><<<grid, F2_THREADS, F2_SMEM, stream>>>(tq, tc, attn_mask, lse, S, heads, nseq, drop);
-  DPRB_CHECK_CUDA(cudaGetLastError());
+  DPRB_LAUNCH_CHECK();
   return 0;
 }
 
@@ -555,7 +555,7 @@ int attn_bwd_tc2(const void* qkv, const int32_t* attn_mask, const void* ctx, con
     attn_bwd_tc2_kernel<true><<<grid, B2_THREADS, B2_SMEM, stream>>>(tq, tdo, tdq, attn_mask, lse, (const bf16*)ctx, (const bf16*)dctx, S, heads, nseq, drop);
   else
     attn_bwd_tc2_kernel<false><<<grid, B2_THREADS, B2_SMEM, stream>>>(tq, tdo, tdq, attn_mask, lse, (const bf16*)ctx, (const bf16*)dctx, S, heads, nseq, drop);
-  DPRB_CHECK_CUDA(cudaGetLastError());
+  DPRB_LAUNCH_CHECK();
   return 0;
 }
 

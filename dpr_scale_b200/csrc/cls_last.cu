@@ -197,7 +197,7 @@ int attn_cls_fwd(const void* qkv, const int32_t* attn_mask, void* ctx_cls, float
   const Drop drop = drop_from_site(dropout_p, site_seed);
   const int nprob = nseq * heads;
   attn_cls_fwd_kernel<<<(nprob + 7) / 8, 256, 0, stream>>>((const bf16*)qkv, attn_mask, (bf16*)ctx_cls, probs, nseq, S, heads, drop);
-  DPRB_CHECK_CUDA(cudaGetLastError());
+  DPRB_LAUNCH_CHECK();
   return 0;
 }
 
@@ -208,7 +208,7 @@ int attn_cls_bwd(const void* qkv, const float* probs, const void* dctx_cls, void
   const Drop drop = drop_from_site(dropout_p, site_seed);
   const int nprob = nseq * heads;
   attn_cls_bwd_kernel<<<(nprob + 7) / 8, 256, 0, stream>>>((const bf16*)qkv, probs, (const bf16*)dctx_cls, (bf16*)dqkv, nseq, S, heads, drop);
-  DPRB_CHECK_CUDA(cudaGetLastError());
+  DPRB_LAUNCH_CHECK();
   return 0;
 }
 
@@ -217,7 +217,7 @@ int add_rows_bf16(void* dst, const void* src, int nrows, int H, long long stride
   if (nrows == 0) return 0;
   const long long n = (long long)nrows * (H / 8);
   add_rows_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>((bf16*)dst, (const bf16*)src, nrows, H, stride_rows);
-  DPRB_CHECK_CUDA(cudaGetLastError());
+  DPRB_LAUNCH_CHECK();
   return 0;
 }
 

@@ -36,6 +36,15 @@ void set_last_error(const char* fmt, ...);
 
 int num_sms();  // cached SM count of the current device
 
+// Every kernel launch of the library goes through this (one call per <<<>>> / cudaLaunchKernelEx): the running total is
+// exported as dprb_launch_count() so callers can report a MEASURED launch count instead of an estimate.
+void count_launch();
+#define DPRB_LAUNCH_CHECK()                \
+  do {                                     \
+    dprb::count_launch();                  \
+    DPRB_CHECK_CUDA(cudaGetLastError());   \
+  } while (0)
+
 // ---------------------------------------------------------------- small device helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

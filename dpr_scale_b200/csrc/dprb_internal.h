@@ -66,6 +66,7 @@ int adamw_step(float* p, const float* g, float* m, float* v, void* shadow, long 
                float beta2, float eps, float wd, int step, float grad_scale, const float* sumsq, float max_norm,
                cudaStream_t stream);
 int cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t stream);
+int cast_bf16_f32(const void* src, float* dst, long long n, cudaStream_t stream);
 
 long long search_workspace_bytes(long long Q, int k);
 int search_topk(const void* queries, const void* corpus, int dtype, long long Q, long long N, int d, int k,

@@ -393,7 +393,7 @@ int embed_ln_fwd(const int64_t* ids, const int64_t* type_ids, const int64_t* pos
 #define CALL(C) ln_fwd_kernel<C, true><<<grid, THREADS, 0, stream>>>(nullptr, ids, type_ids, pos_ids, word, pos, type, gamma, beta, (bf16*)y, stats, nullptr, 1, T, H, eps, drop)
   DISPATCH_MAXC(H, CALL);
 #undef CALL
-  DPRB_CHECK_CUDA(cudaGetLastError());
+  DPRB_LAUNCH_CHECK();
   return 0;
 }
 
@@ -406,7 +406,7 @@ int ln_fwd(const void* z, const float* gamma, const float* beta, void* y, float*
 #define CALL(C) ln_fwd_kernel<C, false><<<grid, THREADS, 0, stream>>>((const bf16*)z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, gamma, beta, (bf16*)y, stats, cls_out, cls_stride > 0 ? cls_stride : 1, T, H, eps, Drop{0u, 0u, 1.f, 1u})
   DISPATCH_MAXC(H, CALL);
 #undef CALL
-  DPRB_CHECK_CUDA(cudaGetLastError());
+  DPRB_LAUNCH_CHECK();
   return 0;
 }
 
@@ -435,7 +435,7 @@ int ln_bwd(const void* dy, const float* dy_cls, int cls_stride, const void* z, c
 #define CALL(C) ln_bwd_kernel<C, false><<<grid, THREADS, smem, stream>>>((const bf16*)dy, dy_cls, cls_stride > 0 ? cls_stride : 1, (const bf16*)z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stats, gamma, (bf16*)dz, nullptr, nullptr, nullptr, dgamma, dbeta, dbias, T, H, (bf16*)dzm, drop)
   DISPATCH_MAXC(H, CALL);
 #undef CALL
-  DPRB_CHECK_CUDA(cudaGetLastError());
+  DPRB_LAUNCH_CHECK();
   return 0;
 }
 
@@ -451,7 +451,7 @@ int embed_ln_bwd(const void* dy, const int64_t* ids, const int64_t* type_ids, co
 #define CALL(C) ln_bwd_kernel<C, true><<<grid, THREADS, smem, stream>>>((const bf16*)dy, nullptr, 1, nullptr, ids, type_ids, pos_ids, word, pos, type, stats, gamma, nullptr, dword, dpos, dtype, dgamma, dbeta, nullptr, T, H, nullptr, drop)
   DISPATCH_MAXC(H, CALL);
 #undef CALL
-  DPRB_CHECK_CUDA(cudaGetLastError());
+  DPRB_LAUNCH_CHECK();
   return 0;
 }
 
@@ -472,7 +472,7 @@ int dropout_mask(uint8_t* out, long long rows, int cols, float p, unsigned long 
   const Drop d = make_drop(p, seed, layer, site);
   const long long n = rows * cols;
   dropout_mask_kernel<<<(int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, stream>>>(out, rows, cols, d);
-  DPRB_CHECK_CUDA(cudaGetLastError());
+  DPRB_LAUNCH_CHECK();
   return 0;
 }
 
@@ -488,7 +488,7 @@ int colsum_bf16(const void* x, long long ld, float* out, int T, int N, cudaStrea
   row_chunks = (T + rows_per_cta - 1) / rows_per_cta;
   dim3 grid(col_blocks, row_chunks);
   colsum_kernel<<<grid, THREADS, 0, stream>>>((const bf16*)x, ld, out, T, N, rows_per_cta);
-  DPRB_CHECK_CUDA(cudaGetLastError());
+  DPRB_LAUNCH_CHECK();
   return 0;
 }
 

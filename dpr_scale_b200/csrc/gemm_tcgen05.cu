@@ -674,6 +674,7 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long l
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    count_launch();
     DPRB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, td2, p));
     if (prof) {
       DPRB_CHECK_CUDA(cudaEventRecord(g_prof.ev[g_prof.used + 1], stream));

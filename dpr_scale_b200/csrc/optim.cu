@@ -93,6 +93,20 @@ cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) 
   }
 }
 
+__global__ void __launch_bounds__(256)
+uncast_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uint2 s2 = reinterpret_cast<const uint2*>(src)[i];
+    const float2 a = unpack_bf16x2(s2.x), b = unpack_bf16x2(s2.y);
+    reinterpret_cast<float4*>(dst)[i] = make_float4(a.x, a.y, b.x, b.y);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = (n4 << 2) + threadIdx.x;
+    dst[i] = __bfloat162float(src[i]);
+  }
+}
+
 int stream_grid(long long n4) {
   int sms = num_sms();
   if (sms <= 0) sms = 148;
@@ -108,7 +122,7 @@ int sumsq_f32(const float* g, long long n, float* out, cudaStream_t stream) {
   DPRB_REQUIRE(n >= 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0, "sumsq: buffer must be 16-byte aligned");
   if (n == 0) return 0;
   sumsq_kernel<<<stream_grid(n >> 2), 256, 0, stream>>>(g, n, out);
-  DPRB_CHECK_CUDA(cudaGetLastError());
+  DPRB_LAUNCH_CHECK();
   return 0;
 }
 
@@ -126,7 +140,7 @@ int adamw_step(float* p, const float* g, float* m, float* v, void* shadow, long 
   a.bc2_rsqrt = 1.f / sqrtf(1.f - powf(beta2, (float)step));
   a.grad_scale = grad_scale; a.max_norm = max_norm;
   adamw_kernel<<<stream_grid(n >> 2), 256, 0, stream>>>(p, g, m, v, (bf16*)shadow, n, a, sumsq);
-  DPRB_CHECK_CUDA(cudaGetLastError());
+  DPRB_LAUNCH_CHECK();
   return 0;
 }
 
@@ -135,7 +149,16 @@ int cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t stream)
                "cast_f32_bf16: buffers must be 16/8-byte aligned");
   if (n == 0) return 0;
   cast_kernel<<<stream_grid(n >> 2), 256, 0, stream>>>(src, (bf16*)dst, n);
-  DPRB_CHECK_CUDA(cudaGetLastError());
+  DPRB_LAUNCH_CHECK();
+  return 0;
+}
+
+int cast_bf16_f32(const void* src, float* dst, long long n, cudaStream_t stream) {
+  DPRB_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 7) == 0,
+               "cast_bf16_f32: buffers must be 8/16-byte aligned");
+  if (n == 0) return 0;
+  uncast_kernel<<<stream_grid(n >> 2), 256, 0, stream>>>((const bf16*)src, dst, n);
+  DPRB_LAUNCH_CHECK();
   return 0;
 }
 

@@ -247,10 +247,10 @@ int score_ce_fwd(const float* q, const float* c, const uint8_t* col_mask, const 
   dim3 grid(row_blocks, splits);
   score_ce_fwd_kernel<<<grid, FWD_WARPS * 32, smem, stream>>>(q, c, col_mask, pair_mask, labels, inv_t, lse, loss_sum,
                                                               logits, Q, C, d, cols_per_split);
-  DPRB_CHECK_CUDA(cudaGetLastError());
+  DPRB_LAUNCH_CHECK();
   if (splits > 1) {
     score_lse_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(logits, labels, lse, loss_sum, Q, C);
-    DPRB_CHECK_CUDA(cudaGetLastError());
+    DPRB_LAUNCH_CHECK();
   }
   return 0;
 }
@@ -274,7 +274,7 @@ int score_ce_bwd(const float* q, const float* c, const float* logits, const int6
     if (z > 1) DPRB_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)na * d * sizeof(float), stream));
     dim3 grid((na + AB - 1) / AB, (d + 255) / 256, z);
     kern<<<grid, 256, 0, stream>>>(logits, lse, labels, X, scale, out, Q, C, d, a0, na, per);
-    DPRB_CHECK_CUDA(cudaGetLastError());
+    DPRB_LAUNCH_CHECK();
     return 0;
   };
   if (nq > 0 && dq != nullptr)

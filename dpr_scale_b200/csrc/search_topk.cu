@@ -542,7 +542,7 @@ int launch_select(const SelectParams& sp, long long Q, cudaStream_t stream) {
     attr_set = true;
   }
   select_topk_kernel<<<(unsigned)Q, SEL_THREADS, smem, stream>>>(sp);
-  DPRB_CHECK_CUDA(cudaGetLastError());
+  DPRB_LAUNCH_CHECK();
   return 0;
 }
 
@@ -616,7 +616,7 @@ int search_topk(const void* queries, const void* corpus, int dtype, long long Q,
     dim3 grid((unsigned)parts, (unsigned)nb);
     if (cap == 512) search_topk_kernel<16><<<grid, THREADS, SMEM_BYTES, stream>>>(tq, tc, sp);
     else search_topk_kernel<64><<<grid, THREADS, SMEM_BYTES, stream>>>(tq, tc, sp);
-    DPRB_CHECK_CUDA(cudaGetLastError());
+    DPRB_LAUNCH_CHECK();
     SelectParams sl;
     const long long qpad = (long long)nb * QT;
     sl.lists = queues; sl.counts = counts; sl.num_lists = (int)parts;
@@ -641,7 +641,7 @@ int topk_merge(const float* scores, const long long* index, long long Q, int tot
   u64* keys = static_cast<u64*>(workspace);
   const long long n = Q * total;
   pack_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(scores, keys, n, total);
-  DPRB_CHECK_CUDA(cudaGetLastError());
+  DPRB_LAUNCH_CHECK();
   SelectParams sl;
   sl.lists = keys; sl.counts = nullptr; sl.num_lists = 1; sl.list_stride = 0; sl.query_stride = total;
   sl.count_stride = 0; sl.fixed_count = total; sl.k = k; sl.kpad = kpad_for(k); sl.index_offset = 0;

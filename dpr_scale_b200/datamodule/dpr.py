@@ -312,6 +312,20 @@ class DenseRetrieverDataModuleBase(LightningDataModule):
             return contiguous_shard_indices(n, world, tr.global_rank, per_node, True, 0, self.epoch, False)
         return list(range(n))
 
+    def _eval_order(self, split):
+        """Lightning (replace_sampler_ddp, the reference's default) wraps the un-sampled val / test loaders of
+        datamodule/dpr.py:197-216 in DistributedSampler(shuffle=False): rank r reads rows r, r+W, r+2W, ... of the row
+        range padded (by wrapping around) to a multiple of W.  Single process: the plain row order."""
+        n = len(self.datasets[split])
+        tr = getattr(self, "trainer", None)
+        world = getattr(tr, "world_size", 1) if tr is not None else 1
+        if world and world > 1 and n > 0:
+            total = math.ceil(n / world) * world
+            idx = list(range(n))
+            idx += (idx * math.ceil((total - n) / n))[:total - n]
+            return idx[tr.global_rank:total:world]
+        return list(range(n))
+
     def _stream(self, split, order, batch_size, collate):
         return BatchStream(self.datasets[split], order, batch_size, collate, drop_last=False,
                            prefetch_batches=self.prefetch_batches, device=self._device())
@@ -320,12 +334,10 @@ class DenseRetrieverDataModuleBase(LightningDataModule):
         return self._stream("train", self._train_order, self.batch_size, self.collate_train)
 
     def val_dataloader(self):
-        return self._stream("valid", lambda: list(range(len(self.datasets["valid"]))), self.val_batch_size,
-                            self.collate_eval)
+        return self._stream("valid", lambda: self._eval_order("valid"), self.val_batch_size, self.collate_eval)
 
     def test_dataloader(self):
-        return self._stream("test", lambda: list(range(len(self.datasets["test"]))), self.test_batch_size,
-                            self.collate_test)
+        return self._stream("test", lambda: self._eval_order("test"), self.test_batch_size, self.collate_test)
 
     def collate_eval(self, batch):
         return self.collate(batch, "eval")

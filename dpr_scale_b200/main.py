@@ -5,14 +5,32 @@ composer (utils/config.py) and mini trainer (trainer.py).
 
   python -m dpr_scale_b200.main --config-name msmarco_baseline task.model.model_path=/path/to/bert datamodule.train_path=...
 """
+import os
 import sys
+
+import torch
+import torch.distributed as dist
 
 from .trainer import Trainer
 from .utils.config import compose, instantiate
 
 
+def init_distributed():
+    """One process per GPU under torchrun: bind the device and join the NCCL group BEFORE the Trainer reads the world
+    size (what Lightning's DDP strategy does inside `Trainer.fit`, main.py:32-44 of the reference).  Without it every
+    rank would train alone on cuda:0."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and not dist.is_initialized():
+        backend = os.environ.get("DPRB_DIST_BACKEND", "nccl" if torch.cuda.is_available() else "gloo")
+        if torch.cuda.is_available():
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group(backend)
+    return world
+
+
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
+    init_distributed()
     name = "config"
     if "--config-name" in argv:
         i = argv.index("--config-name")

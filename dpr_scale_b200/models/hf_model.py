@@ -135,8 +135,15 @@ class _EncoderFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dpooled):
-        ctx.enc._run_backward(ctx.state, dpooled.contiguous().float())
+        enc, state = ctx.enc, ctx.state
         ctx.state = None
+        try:
+            # shared_model=True: the same encoder back-propagates twice per step into one gradient arena; only the
+            # LAST outstanding backward may hand finished slices to the trainer's all-reduce (trainer.py)
+            enc._run_backward(state, dpooled.contiguous().float(), sync=enc._pending_bwd <= 1)
+        finally:
+            enc._pending_bwd = max(0, enc._pending_bwd - 1)
+            state.release()
         return None, None, None, None
 
 
@@ -163,11 +170,66 @@ class _ChunkedEncoderFn(torch.autograd.Function):
         enc, tokens, chunk = ctx.enc, ctx.tokens, ctx.chunk
         dpooled = dpooled.contiguous().float()
         n = tokens["input_ids"].shape[0]
-        for i, lo in enumerate(range(0, n, chunk)):
-            part = {k: v[lo:lo + chunk] for k, v in tokens.items() if v is not None}
-            _, state = enc._run_forward(part, True, train_dropout=True, force_seed=ctx.seeds[i])
-            enc._run_backward(state, dpooled[lo:lo + chunk].contiguous())
+        starts = list(range(0, n, chunk))
+        try:
+            for i, lo in enumerate(starts):
+                part = {k: v[lo:lo + chunk] for k, v in tokens.items() if v is not None}
+                _, state = enc._run_forward(part, True, train_dropout=True, force_seed=ctx.seeds[i])
+                # every chunk accumulates into the same arena: only the last chunk of the last outstanding backward
+                # may release slices to the gradient all-reduce
+                last = (i == len(starts) - 1) and enc._pending_bwd <= 1
+                enc._run_backward(state, dpooled[lo:lo + chunk].contiguous(), sync=last)
+                state.release()
+        finally:
+            enc._pending_bwd = max(0, enc._pending_bwd - 1)
         return None, None, None, None
+
+
+class _FwdState:
+    """What one forward hands to its backward: the C structs, the token tensors they point into, and a LEASE on the
+    activation workspace.  The workspace goes back to the encoder's pool when the state is released (end of backward)
+    or garbage-collected (a forward whose graph is dropped) - never while a backward may still read it, so two live
+    forwards of one encoder (shared_model=True: query + context pass of equal shape) cannot alias."""
+
+    __slots__ = ("w", "b", "keep", "ws", "_pool")
+
+    def __init__(self, w, b, keep, ws, pool):
+        self.w, self.b, self.keep, self.ws, self._pool = w, b, keep, ws, pool
+
+    def release(self):
+        ws, pool = self.ws, self._pool
+        self.ws = self._pool = None
+        if ws is not None and pool is not None:
+            pool.give_back(ws)
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+class _WorkspacePool:
+    """At most ONE idle buffer is kept (they are tens of GB); a lease takes it when it is large enough."""
+
+    def __init__(self):
+        self.idle = None
+        self.leased = 0
+
+    def lease(self, nbytes, device):
+        buf = self.idle
+        if buf is not None and buf.numel() >= nbytes and buf.device == device:
+            self.idle = None
+        else:
+            self.idle = None          # too small / wrong device: let the allocator have it back first
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.leased += 1
+        return buf
+
+    def give_back(self, buf):
+        self.leased -= 1
+        if self.idle is None or self.idle.numel() < buf.numel():
+            self.idle = buf
 
 
 class _Transformer(nn.Module):
@@ -183,6 +245,15 @@ class _Transformer(nn.Module):
         # HF's pooler is part of the reference state_dict but never used (hf_model.py:39) and gets no grad.
         self.add_module("pooler", nn.Module())
         self.pooler.add_module("dense", nn.Linear(H, H))
+        # Checkpoints written with the reference's pinned transformers==3.4.0 carry the persistent buffer
+        # `embeddings.position_ids` (later releases made it non-persistent); it holds arange(max_pos) and is not a
+        # weight, so it is dropped on load instead of failing a strict load_state_dict.
+        self._register_load_state_dict_pre_hook(self._drop_position_ids)
+
+    @staticmethod
+    def _drop_position_ids(state_dict, prefix, *unused):
+        for k in (prefix + "embeddings.position_ids", prefix + "embeddings.token_type_ids"):
+            state_dict.pop(k, None)
 
     def _bind(self, master):
         """(Re)create every parameter as a view into `master`."""
@@ -233,7 +304,9 @@ class HFEncoder(nn.Module):
             linear = nn.Linear(cfg["hidden_size"], projection_dim)
             linear.weight.data.normal_(mean=0.0, std=0.02)
             self.project = nn.Sequential(linear, nn.LayerNorm(projection_dim))
-        self._ws_cache = {}
+        self._ws_cache = {}                  # forward-only workspaces (consumed before forward returns)
+        self._ws_pool = _WorkspacePool()     # save-for-backward workspaces, leased per live forward
+        self._pending_bwd = 0                # forwards of this step whose backward has not run yet
         self._warned_dropout = False
         self.launches = 0
         # multi-GPU hook (set by the trainer): backward runs in `bwd_chunk_layers`-layer chunks and calls
@@ -343,6 +416,7 @@ class HFEncoder(nn.Module):
         # gradients live in the flat arena (kernels accumulate with atomics): always zero in place
         if self.transformer._grads is not None:
             self.transformer._grads.zero_()
+        self._pending_bwd = 0   # a forward that was never back-propagated must not block next step's gradient sync
         for p in self.project.parameters():
             p.grad = None
 
@@ -356,16 +430,20 @@ class HFEncoder(nn.Module):
         return w
 
     def _workspace(self, nseq, S, save):
-        key = (nseq, S, save)
+        w = self._weights_struct(False)
+        nbytes = _lib.load().dprb_encoder_workspace_bytes(ctypes.byref(w), nseq, S, int(save))
+        if nbytes < 0:
+            check(1, "dprb_encoder_workspace_bytes")
+        if save:
+            # saved activations live here until backward: one lease per live forward (see _FwdState)
+            return self._ws_pool.lease(nbytes + 256, self.master.device)
+        # forward-only: the buffer is dead when forward returns (the pooled output is a separate tensor), so one
+        # cached buffer per stream is enough; shapes vary batch to batch (pad-to-longest) and the buffers are large
+        key = torch.cuda.current_stream().cuda_stream
         ws = self._ws_cache.get(key)
-        if ws is None:
-            w = self._weights_struct(False)
-            nbytes = _lib.load().dprb_encoder_workspace_bytes(ctypes.byref(w), nseq, S, int(save))
-            if nbytes < 0:
-                check(1, "dprb_encoder_workspace_bytes")
+        if ws is None or ws.numel() < nbytes + 256 or ws.device != self.master.device:
+            self._ws_cache.pop(key, None)
             ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.master.device)
-            # one live workspace per mode: shapes vary batch to batch (pad-to-longest) and they are large
-            self._ws_cache = {k: v for k, v in self._ws_cache.items() if k[2] != save}
             self._ws_cache[key] = ws
         return ws
 
@@ -414,26 +492,26 @@ class HFEncoder(nn.Module):
               "dprb_encoder_fwd")
         L = self.config["num_hidden_layers"]
         self.launches += 1 + 7 * L
-        ops._count(1 + 7 * L)
-        return pooled, (w, b, (ids, tt, pos, am, ws))
+        return pooled, _FwdState(w, b, (ids, tt, pos, am), ws if save else None, self._ws_pool if save else None)
 
-    def _run_backward(self, state, dpooled):
-        w, b, keep = state
+    def _run_backward(self, state, dpooled, sync=True):
+        w, b = state.w, state.b
         L = self.config["num_hidden_layers"]
         stream = torch.cuda.current_stream().cuda_stream
         lay = self.transformer.layout
-        if self.grad_sync is not None and self.bwd_chunk_layers > 0:
+        sync = sync and self.grad_sync is not None
+        if sync and self.bwd_chunk_layers > 0:
+            # buckets of `step` layers from the top; the last bucket is layer 0 alone, because it also carries the
+            # embedding tables (22 % of BERT-base) and is the only one whose all-reduce cannot hide behind backward
             step = self.bwd_chunk_layers
-            bounds = [(max(0, hi - step), hi) for hi in range(L, 0, -step)]
+            bounds = [(max(1, hi - step), hi) for hi in range(L, 1, -step)] + [(0, 1)]
+            bounds = [b for b in bounds if b[0] < b[1]]
         else:
             bounds = [(0, L)]
         for lo, hi in bounds:
             check(_lib.load().dprb_encoder_bwd(ctypes.byref(w), ctypes.byref(b), dpooled.data_ptr(), lo, hi, stream),
                   "dprb_encoder_bwd")
-            n = 11 * (hi - lo) + (2 if hi == L else 0) + (1 if lo == 0 else 0)  # kernels launched by this call
-            self.launches += n
-            ops._count(n)
-            if self.grad_sync is not None:
+            if sync:
                 e_lo = 0 if lo == 0 else lay.off_layer0 + lo * lay.layer_stride  # lo == 0 also finishes the embeddings
                 self.grad_sync(self, e_lo, lay.off_layer0 + hi * lay.layer_stride)
 
@@ -446,8 +524,10 @@ class HFEncoder(nn.Module):
             n = tokens["input_ids"].shape[0]
             if self.activation_chunk and n > self.activation_chunk:
                 tk = {k: tokens[k] for k in ("input_ids", "token_type_ids", "attention_mask") if k in tokens}
+                self._pending_bwd += 1
                 rep = _ChunkedEncoderFn.apply(anchor, self, tk, self.activation_chunk)
             else:
+                self._pending_bwd += 1
                 rep = _EncoderFn.apply(anchor, self, tokens, True)
         else:
             rep, _ = self._run_forward(tokens, False)

@@ -10,12 +10,13 @@ from ._lib import check
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_DGELU, EPI_F32_ATOMIC_ADD, EPI_F32_STORE = range(6)
 
-LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+def launch_count():
+    """Kernels launched by libdprb.so in this process so far (counted inside the C launchers)."""
+    return int(_lib.load().dprb_launch_count())
 
 
-def _count(n=1):
-    global LAUNCHES
-    LAUNCHES += n
+def _count(n=1):  # kept as a no-op hook: launches are counted in C (dprb_launch_count), not estimated here
+    pass
 
 
 def _ptr(t):
@@ -179,6 +180,11 @@ def adamw_step(p, g, m, v, shadow, lr, beta1, beta2, eps, weight_decay, step, gr
 def cast_f32_bf16(src, dst):
     check(_lib.load().dprb_cast_f32_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()), "dprb_cast_f32_bf16")
     _count()
+    return dst
+
+
+def cast_bf16_f32(src, dst):
+    check(_lib.load().dprb_cast_bf16_f32(_ptr(src), _ptr(dst), src.numel(), _stream()), "dprb_cast_bf16_f32")
     return dst
 
 

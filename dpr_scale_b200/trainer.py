@@ -10,6 +10,7 @@ import os
 import torch
 import torch.distributed as dist
 
+from . import ops
 from .utils.lightning_shim import DDPStrategy
 
 
@@ -67,10 +68,18 @@ class Trainer:
 
     def _sync_slice(self, enc, lo, hi):
         """All-reduce (SUM) grads[lo:hi] of one encoder's flat arena as soon as backward has produced it; NCCL
-        runs it on its own stream, ordered after the kernels enqueued so far, concurrently with the rest of backward."""
+        runs it on its own stream, ordered after the kernels enqueued so far, concurrently with the rest of backward.
+        The encoder calls this only from the LAST outstanding backward over a slice (shared_model=True back-propagates
+        twice into one arena), so every slice is reduced exactly once per step.
+        `fp16_grads` (dpr_task.py:90-92, torch's fp16_compress_hook: cast -> all-reduce -> cast back) is the
+        bf16-compressed form: half the bytes on the wire, fp32 arena before and after."""
         g = enc.grads[lo:hi]
-        if self.compress_grads:
-            h = g.to(torch.bfloat16)
+        if self.compress_grads and g.is_cuda:
+            h = torch.empty(hi - lo, dtype=torch.bfloat16, device=g.device)
+            ops.cast_f32_bf16(g, h)
+            self._pending.append((dist.all_reduce(h, async_op=True), g, h))
+        elif self.compress_grads:
+            h = g.to(torch.bfloat16)   # gloo / CPU tests of the host logic
             self._pending.append((dist.all_reduce(h, async_op=True), g, h))
         else:
             self._pending.append((dist.all_reduce(g, async_op=True), None, None))
@@ -91,7 +100,7 @@ class Trainer:
         for work, g, h in self._pending:  # issued chunk by chunk during backward (see _sync_slice)
             work.wait()
             if h is not None:
-                g.copy_(h)
+                ops.cast_bf16_f32(h, g) if g.is_cuda else g.copy_(h)
         self._pending = []
         extra = [p for p in self.task.parameters() if p.grad is not None and not self._in_arena(p)]
         for p in extra:
@@ -110,12 +119,19 @@ class Trainer:
         loss = self.task.training_step(batch, batch_idx)
         loss.backward()
         self._allreduce_grads()
-        if not hasattr(self.optimizer, "max_grad_norm") and self.gradient_clip_val > 0:
+        if not hasattr(self.optimizer, "max_grad_norm"):
+            # a plain torch optimizer: the SUM-reduced gradients become DDP's mean here, clipped or not
             if self.world_size > 1:
+                done = set()
+                for e in self._encoders():
+                    if e.transformer._grads is not None:
+                        e.transformer._grads.div_(self.world_size)
+                        done.update(id(p) for _, p, _ in e.transformer.arena_params())
                 for p in self.task.parameters():
-                    if p.grad is not None:
+                    if p.grad is not None and id(p) not in done:
                         p.grad.div_(self.world_size)
-            torch.nn.utils.clip_grad_norm_(self.task.parameters(), self.gradient_clip_val)
+            if self.gradient_clip_val > 0:
+                torch.nn.utils.clip_grad_norm_(self.task.parameters(), self.gradient_clip_val)
         self.optimizer.step()
         self.scheduler.step()
         self.global_step += 1

@@ -9,6 +9,7 @@ Files are Lightning-shaped dicts - ``{"state_dict", "epoch", "global_step", ...}
 import os
 
 import torch
+import torch.distributed as dist
 
 
 class ModelCheckpoint:
@@ -33,6 +34,15 @@ class ModelCheckpoint:
             v += 1
             path = os.path.join(self.dirpath, f"{stem}-v{v}.ckpt")
         return path
+
+    def _agreed_path(self, epoch, step):
+        """One process per GPU: only rank 0 probes the directory (the others would race with its write and could pick
+        a `-vN` name that never exists); the choice is broadcast so `best_k` / `best_model_path` agree on all ranks."""
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return self._new_path(epoch, step)
+        box = [self._new_path(epoch, step) if dist.get_rank() == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
 
     @staticmethod
     def _payload(task, epoch, step, extra=None):
@@ -65,7 +75,7 @@ class ModelCheckpoint:
                 if not self._better(score, self.best_k[worst]):
                     worst = "skip"
             if worst != "skip":
-                path = self._new_path(epoch, step)
+                path = self._agreed_path(epoch, step)
                 if is_writer:
                     payload = self._payload(task, epoch, step, {"monitor": self.monitor, "score": score})
                     self._write(payload, path)

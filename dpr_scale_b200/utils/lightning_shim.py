@@ -47,7 +47,22 @@ except Exception:  # noqa
         def log(self, name, value, **kwargs):
             self.logged[name] = value
 
-        def log_dict(self, d, **kwargs):
+        def log_dict(self, d, sync_dist=False, **kwargs):
+            # Lightning's sync_dist=True reduces every logged value with a mean over the ranks, so that rank-level
+            # callbacks (ModelCheckpoint's monitor) see ONE number.  Values are reduced in place in `d`.
+            if sync_dist and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                keys = sorted(d)
+                dev = None
+                for k in keys:
+                    if torch.is_tensor(d[k]) and d[k].is_cuda:
+                        dev = d[k].device
+                if dev is None and dist.get_backend() == "nccl":
+                    dev = torch.device("cuda", torch.cuda.current_device())
+                vals = torch.tensor([float(d[k]) for k in keys], dtype=torch.float64, device=dev)
+                dist.all_reduce(vals)
+                vals /= dist.get_world_size()
+                for k, v in zip(keys, vals.tolist()):
+                    d[k] = v
             self.logged.update(d)
 
         @property

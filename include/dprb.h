@@ -31,6 +31,10 @@ int dprb_version(void);
 const char* dprb_last_error(void);
 /* SM count of the current device (cached); <=0 when no device. */
 int dprb_num_sms(void);
+/* Number of kernels this library has launched in this process since load (every <<<>>> / cudaLaunchKernelEx site
+ * increments it).  bench.py reports the difference over its timed region as `gpu_launches` - a count, not an estimate.
+ * No reference counterpart (the reference launches through PyTorch). */
+int64_t dprb_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * GEMM (tcgen05 / TMA / TMEM):  D[M,N] = epilogue( alpha * sum_k A(m,k) * B(n,k) )
@@ -155,6 +159,9 @@ int dprb_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_b
                     const float* sumsq, float max_norm, dprb_stream_t stream);
 /* fp32 -> bf16 shadow refresh (after a state_dict load). */
 int dprb_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, dprb_stream_t stream);
+/* bf16 -> fp32: unpacks a bf16-compressed gradient slice after its all-reduce (the `fp16_grads` path:
+ * torch's fp16_compress_hook registered at dpr_scale/task/dpr_task.py:90-92 casts, all-reduces and casts back). */
+int dprb_cast_bf16_f32(const void* src_bf16, float* dst, int64_t n, dprb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Whole-encoder forward / backward: the BertModel stack of modeling_bert.py:628-691 as called from

@@ -5,6 +5,11 @@
   python bench.py --impl reference ...                      # the reference's own CPU path (HF + torch, fp32)
   python bench.py --impl stock ...                          # stock HF + PyTorch on the same GPU (the 1.5x denominator)
 
+The default (b200) line also carries: `stock_gpu` / `vs_stock` (stock HF + PyTorch on the SAME GPU right after our arm -
+the denominator of north_star's 1.5x target), `phases` (CUDA-event time per phase of the step), `selfcheck` (N > 1:
+NCCL parity against the reference-generated goldens before timing) and, at N > 1, `grad_allreduce_bf16` (the same step
+with the `fp16_grads` compressed gradient all-reduce).
+
 A "step" = zero_grad -> both encoders fwd -> (all-gather) -> fused scoring+CE -> backward -> (grad all-reduce)
 -> clip(2.0) + AdamW + LambdaLR, on one synthetic batch of configs[1]/[2]: BERT-base, S=128, 128 queries/GPU,
 1 pos + 7 hard negatives (1024 contexts/GPU), in-batch (global when N>1) negatives.  Prints ONE JSON line.
@@ -148,13 +153,43 @@ def peaks():
 
 
 # --------------------------------------------------------------------------------------- CPU reference path
-def cpu_reference_step_factory(cfg, pairs, n, S, threads):
-    """The reference's own CPU path: HF BertModel x2 (fp32) + reference scoring/CE + clip + torch AdamW."""
-    from oracle import hf_path, task as otask
-    torch.set_num_threads(threads)
+REF_ROOT = "/root/reference"
+
+
+def reference_encoders(cfg, dropout):
+    """(query encoder, context encoder, kind) of the reference path.
+    kind == "reference": the UNMODIFIED /root/reference/dpr_scale/models/hf_model.py:HFEncoder, imported as is and
+    instantiated from a temp `save_pretrained` directory - only possible where /root/reference exists (the authoring
+    container).  kind == "port": oracle/hf_path.CLSEncoder, the same arithmetic (HF AutoModel + CLS pooling) without
+    the reference tree - what the GPU box runs, because a Python reference cannot travel and its sources may not be
+    copied into the repo."""
+    from oracle import hf_path
     hf_cfg = hf_path.make_config(cfg["model_type"], **{k: v for k, v in cfg.items() if k not in ("model_type",)})
     torch.manual_seed(0)
-    qe, ce = hf_path.CLSEncoder(hf_cfg, dropout=0.1), hf_path.CLSEncoder(hf_cfg, dropout=0.1)
+    if os.path.exists(os.path.join(REF_ROOT, "dpr_scale", "models", "hf_model.py")) and not os.environ.get("DPRB_REF_PORT"):
+        import shutil
+        import tempfile
+        from transformers import AutoModel
+        hf_cfg.attention_probs_dropout_prob = hf_cfg.hidden_dropout_prob = dropout
+        d = tempfile.mkdtemp(prefix="dprb_ref_")
+        try:
+            AutoModel.from_config(hf_cfg).save_pretrained(d)
+            sys.path.insert(0, REF_ROOT)
+            from dpr_scale.models.hf_model import HFEncoder as RefEncoder
+            with contextlib.redirect_stdout(sys.stderr), contextlib.redirect_stderr(open(os.devnull, "w")):
+                q, c = RefEncoder(model_path=d, dropout=dropout), RefEncoder(model_path=d, dropout=dropout)
+            return q, c, "reference"
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+    return hf_path.CLSEncoder(hf_cfg, dropout=dropout), hf_path.CLSEncoder(hf_cfg, dropout=dropout), "port"
+
+
+def cpu_reference_step_factory(cfg, pairs, n, S, threads):
+    """The reference's own CPU path: HFEncoder x2 (fp32) + reference scoring/CE + clip + torch AdamW."""
+    from oracle import task as otask
+    torch.set_num_threads(threads)
+    qe, ce, kind = reference_encoders(cfg, 0.1)
+    cpu_reference_step_factory.kind = kind
     params = [p for p in list(qe.parameters()) + list(ce.parameters())]
     opt = torch.optim.AdamW(params, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
     batch = synth_batch(0, cfg, pairs, n, S, pin=False)
@@ -178,7 +213,7 @@ def time_cpu_reference(cfg, pairs, n, S, steps, warmup, threads):
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return pairs * steps / dt, dt / steps
+    return pairs * steps / dt, dt / steps, cpu_reference_step_factory.kind
 
 
 # --------------------------------------------------------------------------------------- main arms
@@ -190,33 +225,35 @@ def run_reference(args, workload):
     threads = usable_cores()
     pairs = args.ref_pairs  # bounded sample of the same workload: `pairs` queries with 1+n contexts each, S tokens
     steps, warmup = args.steps, args.warmup
-    value, spstep = time_cpu_reference(cfg, pairs, n, S, steps, warmup, threads)
+    value, spstep, kind = time_cpu_reference(cfg, pairs, n, S, steps, warmup, threads)
     line = {
         "impl": "reference", "metric": "query+ctx pairs/sec (BERT-base, seq128)", "value": value, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": spstep * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload, "sample_pairs_per_step": pairs, "hard_negatives": n, "seq_len": S,
                    "dropout": 0.1, "optimizer": "torch.optim.AdamW + clip 2.0"},
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
-                         "sample": f"{pairs} pairs/step x {steps} steps of {workload} (HF BertModel x2 fp32, fwd+bwd+AdamW)"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": kind,
+                         "sample": f"{pairs} pairs/step x {steps} steps of {workload} "
+                                   f"({'unmodified reference HFEncoder' if kind == 'reference' else 'HF AutoModel + CLS pooling (port: /root/reference is absent on this box)'}"
+                                   f" x2 fp32, fwd+bwd+clip+AdamW)"},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def run_stock(args, workload):
-    """Stock HF + PyTorch on the GPU: reference precision:16 analogue (bf16 autocast), torch AdamW, clip 2.0."""
-    from oracle import hf_path, task as otask
-    cfg, B, n, S = WORKLOADS[workload]
-    dev = torch.device("cuda", 0)
-    hf_cfg = hf_path.make_config(cfg["model_type"], **{k: v for k, v in cfg.items() if k not in ("model_type",)})
-    torch.manual_seed(0)
-    qe, ce = hf_path.CLSEncoder(hf_cfg, dropout=args.dropout).to(dev), hf_path.CLSEncoder(hf_cfg, dropout=args.dropout).to(dev)
+def time_stock(cfg, B, n, S, dropout, dtype, steps, warmup, dev, sample_clocks=True):
+    """Stock HF + PyTorch on the GPU - the denominator of north_star's 1.5x: the reference's encoder class (see
+    reference_encoders) x2, reference scoring / CE, torch.optim.AdamW(fused), clip_grad_norm_(2.0), under
+    torch.autocast fp16 + GradScaler (= the reference's `precision: 16`, conf/trainer/slurm.yaml:15) or bf16; default
+    SDPA attention; batch pre-staged on the device; CUDA events."""
+    from oracle import task as otask
+    qe, ce, kind = reference_encoders(cfg, dropout)
+    qe, ce = qe.to(dev).train(), ce.to(dev).train()
     params = list(qe.parameters()) + list(ce.parameters())
     opt = torch.optim.AdamW(params, lr=1e-5, fused=True)
     batch = to_device(synth_batch(0, cfg, B, n, S), dev)
-    amp = torch.bfloat16 if args.stock_dtype == "bf16" else torch.float16
+    amp = torch.bfloat16 if dtype == "bf16" else torch.float16
     scaler = torch.amp.GradScaler("cuda", enabled=(amp == torch.float16))
 
     def step():
@@ -231,22 +268,109 @@ def run_stock(args, workload):
         scaler.update()
         return loss
 
-    for _ in range(args.warmup):
+    torch.cuda.reset_peak_memory_stats(dev)
+    for _ in range(warmup):
         step()
     torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index or 0)
+    if sample_clocks:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
-    print(json.dumps({"impl": "stock", "metric": "query+ctx pairs/sec (BERT-base, seq128)", "value": B / (ms / 1e3),
-                      "unit": "pairs/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-                      "dtype": args.stock_dtype, "data": "synthetic", "higher_is_better": True,
-                      "config": {"workload": workload, "dropout": args.dropout, "attn": "sdpa",
-                                 "optimizer": "torch.optim.AdamW(fused) + clip 2.0"},
-                      "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
+    clocks = sampler.stop() if sample_clocks else None
+    ms = e0.elapsed_time(e1) / steps
+    out = {"value": B / (ms / 1e3), "unit": "pairs/s", "ms_per_step": ms, "dtype": dtype, "steps": steps,
+           "warmup": warmup, "encoder": kind, "attn": "sdpa", "dropout": dropout,
+           "optimizer": "torch.optim.AdamW(fused) + clip_grad_norm_ 2.0" + (" + GradScaler" if dtype == "fp16" else ""),
+           "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30, "clocks": clocks}
+    del qe, ce, params, opt, batch
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_stock(args, workload):
+    cfg, B, n, S = WORKLOADS[workload]
+    dev = torch.device("cuda", 0)
+    r = time_stock(cfg, B, n, S, args.dropout, args.stock_dtype, args.steps, args.warmup, dev)
+    r.update({"impl": "stock", "metric": "query+ctx pairs/sec (BERT-base, seq128)", "n_gpus": 1, "data": "synthetic",
+              "higher_is_better": True, "config": {"workload": workload}})
+    print(json.dumps(r))
+
+
+# --------------------------------------------------------------------------------------- multi-GPU self-check
+TINY_CFG = dict(vocab_size=64, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256,
+                max_position_embeddings=40)
+
+
+def selfcheck(world, rank, dev):
+    """NCCL parity BEFORE timing (the 1-GPU test box skips the NCCL pytest): the tiny golden model, one rank-specific
+    batch per rank, global in-batch negatives through the packed all-gather, backward, the trainer's gradient
+    all-reduce - against vectors the UNMODIFIED reference produced under gloo at the same world size
+    (tests/golden/make_golden.py: per-rank loss; sum over ranks of every parameter gradient).  Golden files only: no
+    oracle code runs here.  Gates: |loss - reference| <= 5e-2; global gradient rel-L2 <= 1.5x the reference's own
+    bf16-autocast deviation (recorded in golden_1rank.npz)."""
+    import numpy as np
+    from dpr_scale_b200.task.dpr_task import DenseRetrieverTask
+    from dpr_scale_b200.trainer import Trainer
+    gdir = os.path.join(ROOT, "tests", "golden")
+    name = {2: "golden_2rank.npz", 4: "golden_world4.npz", 8: "golden_world8.npz"}.get(world)
+    if name is None or not os.path.exists(os.path.join(gdir, name)):
+        return {"skipped": f"no reference golden for world size {world}"}
+    z, g1 = np.load(os.path.join(gdir, name)), np.load(os.path.join(gdir, "golden_1rank.npz"))
+    T = float(g1["temperature"])
+    task = DenseRetrieverTask(transform={}, datamodule=None, shared_model=False, softmax_temperature=T,
+                              model={"_target_": "dpr_scale_b200.models.hf_model.HFEncoder.from_config",
+                                     "config": TINY_CFG, "dropout": 0.0},
+                              optim={"_target_": "dpr_scale_b200.optim.FusedAdamW", "lr": 0.0})
+    tr = Trainer(max_steps=10, gradient_clip_val=0.0, device=dev, grad_bucket_layers=1)
+    with contextlib.redirect_stdout(sys.stderr):
+        tr.attach(task, None, "fit")
+    for side, enc in (("q", task.query_encoder), ("c", task.context_encoder)):
+        pre = f"sd_{side}/"
+        enc.load_state_dict({k[len(pre):]: torch.from_numpy(g1[k]) for k in g1.files if k.startswith(pre)})
+    task.train()
+    pre = f"rank{rank}/batch/"
+    flat = {k[len(pre):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(pre)}
+    batch = {"query_ids": {k[len("query_ids/"):]: v for k, v in flat.items() if k.startswith("query_ids/")},
+             "contexts_ids": {k[len("contexts_ids/"):]: v for k, v in flat.items() if k.startswith("contexts_ids/")},
+             "pos_ctx_indices": flat["pos_ctx_indices"], "ctx_mask": flat["ctx_mask"].bool()}
+    tr.optimizer.zero_grad()
+    loss = task.training_step(batch, 0)
+    loss.backward()
+    tr._allreduce_grads()
+    torch.cuda.synchronize()
+    num = den = 0.0
+    for side, enc in (("q", task.query_encoder), ("c", task.context_encoder)):
+        for k, p in enc.named_parameters():
+            if world == 2:
+                a, b = f"rank0/grad_{side}/{k}", f"rank1/grad_{side}/{k}"
+                if a not in z.files:
+                    continue
+                want = torch.from_numpy(z[a]) + torch.from_numpy(z[b])
+            else:
+                a = f"gradsum_{side}/{k}"
+                if a not in z.files:
+                    continue
+                want = torch.from_numpy(z[a])
+            got = p.grad.detach().float().cpu()
+            num += float(((got - want).double() ** 2).sum())
+            den += float((want.double() ** 2).sum())
+    res = torch.tensor([abs(float(loss) - float(z[f"rank{rank}/loss"])), (num / den) ** 0.5], device=dev,
+                       dtype=torch.float64)
+    dist.all_reduce(res, op=dist.ReduceOp.MAX)
+    amp = float(g1["amp_global_rel"])
+    loss_err, grad_rel = float(res[0]), float(res[1])
+    del task, tr
+    return {"ok": bool(loss_err <= 5e-2 and grad_rel <= 1.5 * amp), "world": world, "golden": "tests/golden/" + name,
+            "max_loss_err": loss_err, "max_grad_rel_l2": grad_rel, "gate_grad_rel_l2": 1.5 * amp, "gate_loss": 5e-2,
+            "what": "tiny golden model, per-rank batches, packed all-gather + fused scoring + backward + gradient "
+                    "all-reduce over NCCL vs the unmodified reference under gloo at the same world size"}
 
 
 def dataloader_leg(trainer, dev, B, n, S, steps, warmup):
@@ -302,8 +426,9 @@ def dataloader_leg(trainer, dev, B, n, S, steps, warmup):
 
 def run_b200(args, workload):
     from dpr_scale_b200 import _lib, ops
-    from dpr_scale_b200.task.dpr_task import DenseRetrieverTask
+    from dpr_scale_b200.task.dpr_task import DenseRetrieverTask, _ScoreCE
     from dpr_scale_b200.trainer import Trainer
+    from dpr_scale_b200.utils.phase_timer import PhaseTimer
 
     cfg, B, n, S = WORKLOADS[workload]
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -313,8 +438,14 @@ def run_b200(args, workload):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    check = None
+    if world > 1 and not args.no_selfcheck:
+        check = selfcheck(world, rank, dev)
+        if rank == 0 and not check.get("ok", True):
+            print(f"[bench] MULTI-GPU SELF-CHECK FAILED: {check}", file=sys.stderr)
     task = DenseRetrieverTask(
         transform={}, datamodule=None, shared_model=False, in_batch_negatives=True, warmup_steps=10,
+        fp16_grads=(args.grad_dtype == "bf16"),
         model={"_target_": "dpr_scale_b200.models.hf_model.HFEncoder.from_config", "config": cfg,
                "dropout": args.dropout},
         optim={"_target_": "dpr_scale_b200.optim.FusedAdamW", "lr": 1e-5, "betas": [0.9, 0.999], "eps": 1e-8,
@@ -323,7 +454,7 @@ def run_b200(args, workload):
     with contextlib.redirect_stdout(sys.stderr):      # stdout carries exactly ONE line: the JSON result
         trainer.attach(task, None, "fit")
     task.train()
-    task.context_encoder.activation_chunk = ACT_CHUNK.get(workload, 0)
+    task.context_encoder.activation_chunk = ACT_CHUNK.get(workload, 0) if args.act_chunk < 0 else args.act_chunk
     host_batch = synth_batch(rank, cfg, B, n, S)
     dev_batch = to_device(host_batch, dev)
     lib = _lib.load()
@@ -352,9 +483,9 @@ def run_b200(args, workload):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = ops.LAUNCHES
+    launches0 = ops.launch_count()
     ms_step = timed(lambda i: trainer.training_step(dev_batch, i), args.steps)
-    launches = (ops.LAUNCHES - launches0)
+    launches = ops.launch_count() - launches0        # counted inside the C launchers (dprb_launch_count)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- roofline leg: the same step, timed again with CUDA events around EVERY GEMM launch.  The query encoder is
@@ -363,12 +494,19 @@ def run_b200(args, workload):
     prof_steps = min(args.steps, 5)
     os.environ["DPRB_NO_STREAM_OVERLAP"] = "1"
     trainer.training_step(dev_batch, 0)
-    _lib.check(lib.dprb_gemm_profile_enable(1, 700 * prof_steps + 64), "profile_enable")
+    _lib.check(lib.dprb_gemm_profile_enable(1, 1500 * prof_steps + 64), "profile_enable")
     ms_prof = timed(lambda i: trainer.training_step(dev_batch, i), prof_steps)
     tms, tfl, nl = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
     _lib.check(lib.dprb_gemm_profile_read(ctypes.byref(tms), ctypes.byref(tfl), ctypes.byref(nl)), "profile_read")
     _lib.check(lib.dprb_gemm_profile_enable(0, 0), "profile_disable")
     del os.environ["DPRB_NO_STREAM_OVERLAP"]
+
+    # ---- per-phase leg: CUDA events at the phase boundaries of the step (main stream), rank 0's view
+    pt = PhaseTimer()
+    task.phase_timer = _ScoreCE.phase = pt
+    timed(lambda i: trainer.training_step(dev_batch, i), prof_steps)
+    phases = pt.summary()
+    task.phase_timer = _ScoreCE.phase = None
 
     # ---- end-to-end number: host (pinned) inputs -> H2D each step, loss read back each step
     losses = []
@@ -379,6 +517,17 @@ def run_b200(args, workload):
 
     e2e_step(0)
     ms_e2e = timed(e2e_step, args.steps)
+
+    # ---- N > 1: the same step with the bf16-compressed gradient all-reduce (`fp16_grads`, dpr_task.py:90-92)
+    alt = None
+    if world > 1:
+        other = args.grad_dtype != "bf16"
+        trainer.set_grad_compression(other)
+        trainer.training_step(dev_batch, 0)
+        ms_alt = timed(lambda i: trainer.training_step(dev_batch, i), args.steps)
+        trainer.set_grad_compression(not other)
+        alt = {"value": B * world / (ms_alt / 1e3), "unit": "pairs/s", "ms_per_step": ms_alt,
+               "grad_allreduce": "bf16" if other else "fp32"}
 
     # ---- end-to-end number INCLUDING the dataloader (single GPU; JSONL -> tokeniser -> pinned -> H2D -> step)
     dl = None
@@ -392,10 +541,26 @@ def run_b200(args, workload):
         except Exception as e:  # noqa: the headline numbers above must survive a data-side failure
             dl = {"error": repr(e)[:300]}
 
+    peak_mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+
+    # ---- stock HF + PyTorch on the SAME GPU, right after our arm (the 1.5x denominator), its own clock samples
+    stock = None
+    if world == 1 and not args.no_stock:
+        import gc
+        del trainer, task, dev_batch
+        gc.collect()
+        torch.cuda.empty_cache()
+        stock = {}
+        for dt in ("bf16", "fp16"):
+            try:
+                stock[dt] = time_stock(cfg, B, n, S, args.dropout, dt, min(args.steps, 10), 3, dev)
+            except Exception as e:  # noqa
+                stock[dt] = {"error": repr(e)[:300]}
+
     pairs_step = B * world
     value = pairs_step / (ms_step / 1e3)
     peak_tf, peak_hbm, peak_src = peaks()
@@ -408,35 +573,53 @@ def run_b200(args, workload):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload, "model": ("BERT-base" if cfg is BERT_BASE else "RoBERTa-large") + " x2 (query+context, shared_model=false)",
-                   "activation_chunk": ACT_CHUNK.get(workload, 0),
+                   "activation_chunk": ACT_CHUNK.get(workload, 0) if args.act_chunk < 0 else args.act_chunk,
                    "queries_per_gpu": B, "hard_negatives": n, "contexts_per_gpu": B * (1 + n), "seq_len": S,
                    "global_batch": pairs_step, "parallelism": f"dp{world}", "negatives": "global in-batch" if world > 1 else "in-batch",
                    "optimizer": "fused AdamW + clip 2.0 + LambdaLR", "dropout": args.dropout,
+                   "grad_allreduce": (args.grad_dtype + (" (reference default: fp16_grads=false)" if args.grad_dtype == "fp32" else " (fp16_grads=true)")) if world > 1 else None,
                    "l2": "working set (>=40 GB activations + 0.9 GB weights/step) exceeds the 126 MB L2; no flush needed"},
         "e2e": {"value": pairs_step / (ms_e2e / 1e3), "unit": "pairs/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": batch_bytes(host_batch), "d2h_bytes_per_step": 4},
         "e2e_dataloader": dl,
         "gpu_launches": launches,
+        "gpu_launches_how": "dprb_launch_count(): incremented at every kernel launch inside libdprb.so, difference over the timed region",
         "clocks": clocks,
+        "peak_mem_gb": peak_mem,
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel<*,*,2> (tcgen05 cta_group::2 UMMA 256x256x16)",
                      "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tflops / peak_tf,
                      "peak_source": peak_src,
-                     # ncu --set full (profiles/r1_final_ncu_full_summary.json), largest launch of this kernel
-                     # (FFN-in, M=131072 N=3072 K=768): dram read+write vs its algorithmic bytes (A + 2 outputs + W)
-                     "traffic": 1.766e9 if workload == "bert-base_s128_b128_n7" else None,
-                     "traffic_algorithmic": 1.816e9 if workload == "bert-base_s128_b128_n7" else None,
+                     # not measured by this run: one `ncu --set full` capture of the largest launch of this kernel
+                     # (FFN-in, M=131072 N=3072 K=768), dram read+write vs its algorithmic bytes (A + 2 outputs + W)
+                     "traffic": None,
+                     "traffic_ncu": ({"bytes": 1.766e9, "algorithmic_bytes": 1.816e9, "launch": "FFN-in M131072 N3072 K768",
+                                      "source": "profiles/r1_final_ncu_full_summary.json (ncu --set full, separate run)"}
+                                     if workload == "bert-base_s128_b128_n7" else None),
                      "gemm_launches": nl.value,
                      "gemm_ms_per_step": tms.value / prof_steps, "roofline_region_ms_per_step": ms_prof,
                      "gemm_share_of_step": (tms.value / prof_steps) / ms_prof,
                      "step_model_tflops": step_flops / (ms_step / 1e3) / 1e12,
                      "step_frac_of_peak": step_flops / (ms_step / 1e3) / 1e12 / peak_tf},
+        "phases": {"ms_per_step": phases, "how": "CUDA events on the main stream at phase boundaries, rank 0, "
+                                                 f"{prof_steps} steps; encoders_fwd includes the side-stream query encoder join"},
         "loss_first_last": [losses[0], losses[-1]] if losses else None,
     }
+    if check is not None:
+        line["selfcheck"] = check
+    if alt is not None:
+        line["grad_allreduce_" + alt["grad_allreduce"]] = alt
+    if stock is not None:
+        line["stock_gpu"] = stock
+        ok = [v["value"] for v in stock.values() if "value" in v]
+        if ok:
+            # against the FASTER of the two stock precisions (the conservative ratio)
+            line["vs_stock"] = {"ratio": value / max(ok), "e2e_ratio": line["e2e"]["value"] / max(ok),
+                                "stock_pairs_per_s": max(ok), "target": 1.5}
     if world == 1 and not args.no_cpu_baseline:
         threads = usable_cores()
-        v, sp = time_cpu_reference(cfg, 1, n, S, 2, 1, threads)
-        line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
-                                "sample": f"1 pair/step x 2 steps (+1 warm-up) of {workload}: HF BertModel x2 fp32 "
+        v, sp, kind = time_cpu_reference(cfg, 1, n, S, 2, 1, threads)
+        line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": threads, "kind": kind,
+                                "sample": f"1 pair/step x 2 steps (+1 warm-up) of {workload}: reference encoder class x2 fp32 "
                                           f"fwd+bwd+clip+AdamW on {threads} host threads"}
     print(json.dumps(line))
     if world > 1:
@@ -456,6 +639,11 @@ def main():
     ap.add_argument("--dropout", type=float, default=0.1,
                     help="hidden + attention dropout of both encoders (reference default 0.1, conf/task/model/hf_model.yaml:5)")
     ap.add_argument("--stock-dtype", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--no-stock", action="store_true", help="skip the stock HF + PyTorch leg of the default line")
+    ap.add_argument("--no-selfcheck", action="store_true", help="skip the NCCL parity self-check at N > 1")
+    ap.add_argument("--grad-dtype", default="fp32", choices=["fp32", "bf16"],
+                    help="gradient all-reduce precision at N > 1 (fp32 = the reference default fp16_grads=false)")
+    ap.add_argument("--act-chunk", type=int, default=-1, help="override the activation chunk (sequences) of the context encoder")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args, args.workload)

@@ -68,6 +68,12 @@ SIGNATURES = {
     "dprb_score_ce_fwd": (c_int, [_P, _P, _P, _P, _P, c_float, _P, _P, _P, c_int, c_int, c_int, _P]),
     "dprb_score_ce_bwd": (c_int, [_P, _P, _P, _P, _P, c_float, c_float, _P, _P, c_int, c_int, c_int, c_int,
                                   c_int, c_int, c_int, _P]),
+    "dprb_score_tc_supported": (c_int, [c_int, c_int, c_int]),
+    "dprb_score_tc_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int]),
+    "dprb_score_tc_fwd": (c_int, [_P, _P, _P, _P, _P, c_float, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int64,
+                                  _P]),
+    "dprb_score_tc_bwd": (c_int, [_P, _P, _P, _P, c_float, c_float, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
+                                  c_int, _P, c_int64, _P]),
     "dprb_sumsq_f32": (c_int, [_P, c_int64, _P, _P]),
     "dprb_adamw_step": (c_int, [_P, _P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int,
                                 c_float, _P, c_float, _P]),

@@ -114,6 +114,22 @@ int dprb_score_ce_bwd(const float* q, const float* c, const float* logits, const
   return score_ce_bwd(q, c, logits, labels, lse, grad_scale, inv_temperature, dq, dc, Q, C, d, q0, nq, c0, nc,
                       S(stream));
 }
+int dprb_score_tc_supported(int Q, int C, int d) { return score_tc_supported(Q, C, d) ? 1 : 0; }
+int64_t dprb_score_tc_workspace_bytes(int Q, int C, int d, int nq, int nc) {
+  return score_tc_workspace_bytes(Q, C, d, nq, nc);
+}
+int dprb_score_tc_fwd(const float* q, const float* c, const uint8_t* col_mask, const uint8_t* pair_mask,
+                      const int64_t* labels, float inv_temperature, float* lse, float* loss_sum, float* logits, int Q,
+                      int C, int d, int nq, int nc, void* workspace, int64_t workspace_bytes, dprb_stream_t stream) {
+  return score_tc_fwd(q, c, col_mask, pair_mask, labels, inv_temperature, lse, loss_sum, logits, Q, C, d, nq, nc,
+                      workspace, workspace_bytes, S(stream));
+}
+int dprb_score_tc_bwd(const uint8_t* col_mask, const uint8_t* pair_mask, const int64_t* labels, const float* lse,
+                      float grad_scale, float inv_temperature, float* dq, float* dc, int Q, int C, int d, int q0, int nq,
+                      int c0, int nc, void* workspace, int64_t workspace_bytes, dprb_stream_t stream) {
+  return score_tc_bwd(col_mask, pair_mask, labels, lse, grad_scale, inv_temperature, dq, dc, Q, C, d, q0, nq, c0, nc,
+                      workspace, workspace_bytes, S(stream));
+}
 int dprb_sumsq_f32(const float* g, int64_t n, float* out, dprb_stream_t stream) {
   return sumsq_f32(g, n, out, S(stream));
 }

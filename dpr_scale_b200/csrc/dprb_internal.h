@@ -61,6 +61,15 @@ int score_ce_bwd(const float* q, const float* c, const float* logits, const int6
                  float grad_scale, float inv_t, float* dq, float* dc, int Q, int C, int d, int q0, int nq, int c0,
                  int nc, cudaStream_t stream);
 
+bool score_tc_supported(int Q, int C, int d);
+long long score_tc_workspace_bytes(int Q, int C, int d, int nq, int nc);
+int score_tc_fwd(const float* q, const float* c, const uint8_t* col_mask, const uint8_t* pair_mask,
+                 const int64_t* labels, float inv_t, float* lse, float* loss_sum, float* logits, int Q, int C, int d,
+                 int nq, int nc, void* workspace, long long workspace_bytes, cudaStream_t stream);
+int score_tc_bwd(const uint8_t* col_mask, const uint8_t* pair_mask, const int64_t* labels, const float* lse,
+                 float grad_scale, float inv_t, float* dq, float* dc, int Q, int C, int d, int q0, int nq, int c0, int nc,
+                 void* workspace, long long workspace_bytes, cudaStream_t stream);
+
 int sumsq_f32(const float* g, long long n, float* out, cudaStream_t stream);
 int adamw_step(float* p, const float* g, float* m, float* v, void* shadow, long long n, float lr, float beta1,
                float beta2, float eps, float wd, int step, float grad_scale, const float* sumsq, float max_norm,

@@ -185,6 +185,46 @@ class _ChunkedEncoderFn(torch.autograd.Function):
         return None, None, None, None
 
 
+class _ProjectFn(torch.autograd.Function):
+    """``project = Sequential(Linear(H, p), LayerNorm(p))`` of hf_model.py:26-34 on the dprb kernels:
+    pooled fp32 -> bf16 -> tcgen05 GEMM (+bias, bf16 out) -> dprb_ln_fwd whose fp32 row output IS the result;
+    backward: dprb_ln_bwd (fused dgamma / dbeta / Linear-bias gradient) -> wgrad GEMM (fp32 split-K accumulate) and
+    dgrad GEMM (fp32 store) back into the encoder's upstream gradient.  Same precision contract as the encoder body:
+    16-bit GEMM operands, fp32 accumulation, fp32 LayerNorm statistics, fp32 parameters and gradients."""
+
+    @staticmethod
+    def forward(ctx, pooled, weight, bias, gamma, beta, eps):
+        N, H = pooled.shape
+        P = weight.shape[0]
+        if P % 8 or P > 1024 or H % 8:
+            raise ValueError(f"dprb projection head needs projection_dim % 8 == 0 and <= 1024 (got {P})")
+        dev = pooled.device
+        x16 = torch.empty(N, H, dtype=torch.bfloat16, device=dev)
+        w16 = torch.empty(P, H, dtype=torch.bfloat16, device=dev)
+        ops.cast_f32_bf16(pooled.contiguous(), x16)
+        ops.cast_f32_bf16(weight.detach().contiguous(), w16)
+        z = torch.empty(N, P, dtype=torch.bfloat16, device=dev)
+        ops.gemm(x16, w16, z, N, P, H, H, H, P, False, False, ops.EPI_BIAS, bias.detach().contiguous())
+        _, stats, out = ops.ln_fwd(z, gamma.detach().contiguous(), beta.detach().contiguous(), eps, cls_stride=1)
+        ctx.save_for_backward(x16, w16, z, stats, gamma.detach())
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x16, w16, z, stats, gamma = ctx.saved_tensors
+        N, H = x16.shape
+        P = w16.shape[0]
+        dev = x16.device
+        dgamma, dbeta, dbias = (torch.zeros(P, dtype=torch.float32, device=dev) for _ in range(3))
+        dz = ops.ln_bwd(None, z, stats, gamma.contiguous(), dgamma, dbeta, dbias, dy_cls=dout.contiguous().float(),
+                        cls_stride=1)
+        dw = torch.zeros(P, H, dtype=torch.float32, device=dev)
+        ops.gemm(dz, x16, dw, P, H, N, P, H, H, True, True, ops.EPI_F32_ATOMIC_ADD, None, splits=0)
+        dx = torch.empty(N, H, dtype=torch.float32, device=dev)
+        ops.gemm(dz, w16, dx, N, H, P, P, H, H, False, True, ops.EPI_F32_STORE, None)
+        return dx, dw, dbias, dgamma, dbeta, None
+
+
 class _FwdState:
     """What one forward hands to its backward: the C structs, the token tensors they point into, and a LEASE on the
     activation workspace.  The workspace goes back to the encoder's pool when the state is released (end of backward)
@@ -531,5 +571,7 @@ class HFEncoder(nn.Module):
                 rep = _EncoderFn.apply(anchor, self, tokens, True)
         else:
             rep, _ = self._run_forward(tokens, False)
-        rep = self.project(rep)
+        if not isinstance(self.project, nn.Identity):
+            lin, ln = self.project[0], self.project[1]
+            rep = _ProjectFn.apply(rep, lin.weight, lin.bias, ln.weight, ln.bias, ln.eps)
         return rep  # already fresh storage (reference: sentence_rep.clone())

@@ -22,22 +22,35 @@ from ..utils.lightning_shim import DDPShardedStrategy, DDPStrategy, LightningMod
 
 
 class _ScoreCE(torch.autograd.Function):
-    """loss = mean_i CE(q_all @ c_all.T / T with masked columns, labels); grads only for the local slices."""
+    """loss = mean_i CE(q_all @ c_all.T / T with masked columns, labels); grads only for the local slices.
+    Tensor-core path (d % 8 == 0): one fused pass, no logits in HBM, backward recomputes the local tiles.
+    Otherwise: the fp32 FFMA kernels with stored logits."""
+
+    phase = None   # optional utils.phase_timer.PhaseTimer (bench.py's per-phase leg)
 
     @staticmethod
     def forward(ctx, q_local, c_local, q_all, c_all, labels, col_mask, pair_mask, inv_t, q0, c0):
-        loss_sum, lse, logits = ops.score_ce_fwd(q_all, c_all, col_mask, labels, inv_t, True, pair_mask)
-        ctx.save_for_backward(q_all, c_all, logits, labels, lse)
-        ctx.meta = (inv_t, q0, q_local.shape[0], c0, c_local.shape[0])
-        ctx.mark_non_differentiable(logits)
-        return loss_sum[0] / q_all.shape[0], logits
+        nq, nc = q_local.shape[0], c_local.shape[0]
+        loss_sum, lse, logits, sctx = ops.score_fwd(q_all, c_all, col_mask, labels, inv_t, False, pair_mask, (nq, nc))
+        ctx.sctx = sctx
+        if sctx is None:
+            ctx.save_for_backward(q_all, c_all, logits, labels, lse)
+        ctx.meta = (inv_t, q0, nq, c0, nc)
+        return loss_sum[0] / q_all.shape[0]
 
     @staticmethod
-    def backward(ctx, g, _g_logits):
-        q_all, c_all, logits, labels, lse = ctx.saved_tensors
+    def backward(ctx, g):
         inv_t, q0, nq, c0, nc = ctx.meta
-        dq, dc = ops.score_ce_bwd(q_all, c_all, logits, labels, lse, 1.0, inv_t, q0, nq, c0, nc)
-        return dq * g, dc * g, None, None, None, None, None, None, None, None
+        if ctx.sctx is not None:
+            dq, dc = ops.score_bwd(ctx.sctx, 1.0, inv_t, q0, nq, c0, nc)
+            ctx.sctx = None
+        else:
+            q_all, c_all, logits, labels, lse = ctx.saved_tensors
+            dq, dc = ops.score_ce_bwd(q_all, c_all, logits, labels, lse, 1.0, inv_t, q0, nq, c0, nc)
+        dq, dc = dq * g, dc * g
+        if _ScoreCE.phase is not None:
+            _ScoreCE.phase.mark("score_bwd")
+        return dq, dc, None, None, None, None, None, None, None, None
 
 
 class DenseRetrieverTask(LightningModule):
@@ -70,6 +83,7 @@ class DenseRetrieverTask(LightningModule):
         self.pretrained_checkpoint_path = pretrained_checkpoint_path
         self.softmax_temperature = softmax_temperature
         self.setup_done = False
+        self.phase_timer = None   # utils.phase_timer.PhaseTimer while bench.py measures per-phase times
 
     # ------------------------------------------------------------------ model construction
     def setup(self, stage: str):
@@ -189,12 +203,17 @@ class DenseRetrieverTask(LightningModule):
         pos_ctx_indices = batch["pos_ctx_indices"].to(dev, torch.int64)
         mask = batch["ctx_mask"].to(dev)
         query_repr, context_repr = self(query_ids, contexts_ids)
+        pt = self.phase_timer
+        if pt is not None:
+            pt.mark("encoders_fwd")
         inv_t = 1.0 / float(self.softmax_temperature)
         pair_mask = None
         if self.in_batch_negatives:
             if self._is_ddp():
                 q_all, c_all, labels, col_mask, q0, c0 = self._gather_global(query_repr, context_repr,
                                                                             pos_ctx_indices, mask)
+                if pt is not None:
+                    pt.mark("gather")
             else:
                 q_all, c_all, labels = query_repr.detach(), context_repr.detach(), pos_ctx_indices
                 col_mask, q0, c0 = mask.to(torch.uint8), 0, 0
@@ -208,9 +227,11 @@ class DenseRetrieverTask(LightningModule):
             pair_mask = (~inside | mask.unsqueeze(0)).to(torch.uint8).contiguous()
             q_all, c_all, labels = query_repr.detach(), context_repr.detach(), pos_ctx_indices
             col_mask, q0, c0 = None, 0, 0
-        loss, _ = _ScoreCE.apply(query_repr, context_repr, q_all.contiguous(), c_all.contiguous(),
-                                 labels.contiguous(), None if col_mask is None else col_mask.contiguous(),
-                                 pair_mask, inv_t, q0, c0)
+        loss = _ScoreCE.apply(query_repr, context_repr, q_all.contiguous(), c_all.contiguous(),
+                              labels.contiguous(), None if col_mask is None else col_mask.contiguous(),
+                              pair_mask, inv_t, q0, c0)
+        if pt is not None:
+            pt.mark("score_fwd")
         self.log("train_loss", loss, prog_bar=True)
         return loss
 

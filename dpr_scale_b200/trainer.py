@@ -115,10 +115,19 @@ class Trainer:
 
     def training_step(self, batch, batch_idx=0):
         """zero_grad -> task.training_step -> backward -> grad all-reduce -> clip + AdamW -> LR schedule."""
+        pt = getattr(self.task, "phase_timer", None)
+        if pt is not None:
+            pt.begin()
         self.optimizer.zero_grad()
+        if pt is not None:
+            pt.mark("zero_grad")
         loss = self.task.training_step(batch, batch_idx)
         loss.backward()
+        if pt is not None:
+            pt.mark("encoders_bwd")
         self._allreduce_grads()
+        if pt is not None:
+            pt.mark("grad_allreduce_exposed")
         if not hasattr(self.optimizer, "max_grad_norm"):
             # a plain torch optimizer: the SUM-reduced gradients become DDP's mean here, clipped or not
             if self.world_size > 1:
@@ -135,6 +144,9 @@ class Trainer:
         self.optimizer.step()
         self.scheduler.step()
         self.global_step += 1
+        if pt is not None:
+            pt.mark("optimizer")
+            pt.end()
         return loss
 
     # ------------------------------------------------------------------ loops

@@ -146,6 +146,25 @@ int dprb_score_ce_bwd(const float* q, const float* c, const float* logits, const
                       const float* lse, float grad_scale, float inv_temperature, float* dq, float* dc, int Q,
                       int C, int d, int q0, int nq, int c0, int nc, dprb_stream_t stream);
 
+/* The same operator on the tensor cores, in ONE pass (the form BASELINE.json's north_star names): similarity tile via
+ * tcgen05.mma into TMEM, online row max / sum-exp / label pick straight from tcgen05.ld, loss accumulated by the last
+ * tile of each row block; logits reach HBM only if `logits` is non-NULL.  fp32 fidelity comes from an exact 3-way bf16
+ * split of q and c (six partial products per k-block, fp32 accumulate): logits agree with the fp32 product of
+ * dpr_task.py:99 to ~1e-6 relative.  Backward RECOMPUTES the tiles of the rank-local row block and column block
+ * (no stored logits) and runs dq = W_rows c, dc = W_cols^T q on the tcgen05 GEMM.
+ *   nq / nc: the local row / column counts backward will ask for (sizes the workspace; -1 = all).
+ *   workspace: caller-owned, 256-byte aligned, >= dprb_score_tc_workspace_bytes(...); it carries the operand splits
+ *   from the forward call to the backward call of the same step.
+ * Requires d % 8 == 0 (dprb_score_tc_supported); other shapes use dprb_score_ce_fwd/bwd above. */
+int dprb_score_tc_supported(int Q, int C, int d);
+int64_t dprb_score_tc_workspace_bytes(int Q, int C, int d, int nq, int nc);
+int dprb_score_tc_fwd(const float* q, const float* c, const uint8_t* col_mask, const uint8_t* pair_mask,
+                      const int64_t* labels, float inv_temperature, float* lse, float* loss_sum, float* logits, int Q,
+                      int C, int d, int nq, int nc, void* workspace, int64_t workspace_bytes, dprb_stream_t stream);
+int dprb_score_tc_bwd(const uint8_t* col_mask, const uint8_t* pair_mask, const int64_t* labels, const float* lse,
+                      float grad_scale, float inv_temperature, float* dq, float* dc, int Q, int C, int d, int q0, int nq,
+                      int c0, int nc, void* workspace, int64_t workspace_bytes, dprb_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Optimizer step over a flat fp32 parameter arena.  Replaces torch.optim.AdamW
  * (conf/task/optim/adamw.yaml via dpr_task.py:124) + clip_grad_norm_(2.0)

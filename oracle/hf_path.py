@@ -17,8 +17,11 @@ def make_config(kind="bert", **kw):
 class CLSEncoder(nn.Module):
     """AutoModel + last_hidden_state[:, 0, :].clone()  — the arithmetic of HFEncoder.forward."""
 
-    def __init__(self, config, dropout=0.0):
+    def __init__(self, config, dropout=0.0, model=None):
         super().__init__()
+        if model is not None:          # an already built (e.g. seeded, tests/realdims.py) HF module
+            self.transformer = model
+            return
         from transformers import AutoModel
         config.attention_probs_dropout_prob = dropout
         config.hidden_dropout_prob = dropout

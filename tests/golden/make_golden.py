@@ -15,6 +15,11 @@ Cases:
                     away from the saturated-softmax regime where a 0.3 % bf16 logit error swings probabilities by e^1) — embeddings, logits, loss, all grads.
   golden_2rank.npz  same model, world_size 2 (gloo): per-rank loss and per-rank grads (global in-batch negatives).
   golden_roberta.npz RoBERTa-style (pad_id 1, position ids from cumsum) encoder forward only.
+  golden_world4.npz / golden_world8.npz  (`python make_golden.py world 4 8`) same model and per-rank batches at world
+                    size 4 / 8 (gloo): per-rank batch + loss and the SUM over ranks of every parameter gradient - what
+                    the trainer's all-reduce must produce.  bench.py's multi-GPU self-check compares against these
+                    (and against golden_2rank.npz at N = 2) before timing, so NCCL parity is on record in every
+                    scaling run even though the 1-GPU test box skips the NCCL pytest.
 """
 import importlib
 import os
@@ -224,7 +229,31 @@ def run_rank(rank, world, qdir, cdir, port, ret):
         dist.destroy_process_group()
 
 
+def make_world(worlds):
+    import torch.multiprocessing as mp
+    qdir = make_model_dir("bert", 0)
+    cdir = make_model_dir("bert", 0, perturb_seed=1)
+    for W in worlds:
+        shared = mp.Manager().dict()
+        mp.spawn(run_rank, args=(W, qdir, cdir, 29540 + W, shared), nprocs=W, join=True)
+        out = {}
+        for r in range(W):
+            for k, v in shared[r].items():
+                if k.startswith("batch/") or k == "loss":
+                    out[f"rank{r}/{k}"] = v
+                elif k.startswith("grad_"):
+                    key = "gradsum_" + k[len("grad_"):]
+                    out[key] = out[key] + v.astype(np.float64) if key in out else v.astype(np.float64)
+        out = {k: (v.astype(np.float32) if k.startswith("gradsum_") else v) for k, v in out.items()}
+        np.savez_compressed(os.path.join(HERE, f"golden_world{W}.npz"), **out)
+        print(f"world {W} losses", [float(shared[r]["loss"]) for r in range(W)])
+    for d in (qdir, cdir):
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def main():
+    if len(sys.argv) > 2 and sys.argv[1] == "world":
+        return make_world([int(x) for x in sys.argv[2:]])
     qdir = make_model_dir("bert", 0)
     cdir = make_model_dir("bert", 0, perturb_seed=1)
     ret = {}

@@ -208,7 +208,9 @@ def check_attention(nseq=3, S=128, heads=2, masked=True, seed=4, dropout=0.0):
 
 
 # ------------------------------------------------------------------ scoring + CE
-def check_score_ce(Q=37, C=250, d=768, inv_t=2.0, q0=8, nq=16, c0=40, nc=100, seed=5):
+def check_score_ce(Q=37, C=250, d=768, inv_t=2.0, q0=8, nq=16, c0=40, nc=100, seed=5, pair=False):
+    """Fused scoring + CE: the tensor-core single-pass path (d % 8 == 0; tiles recomputed in backward, no logits in HBM
+    unless asked) AND the fp32 FFMA kernels, both against oracle/task.py (dpr_task.py:98-105, :197-212)."""
     g = torch.Generator().manual_seed(seed)
     q = torch.randn(Q, d, generator=g)
     c = torch.randn(C, d, generator=g)
@@ -217,20 +219,42 @@ def check_score_ce(Q=37, C=250, d=768, inv_t=2.0, q0=8, nq=16, c0=40, nc=100, se
     mask[labels] = False
     res = {}
     d_ = lambda t: t.to(DEV)
-    loss_sum, lse, logits = ops.score_ce_fwd(d_(q), d_(c), d_(mask.to(torch.uint8)), d_(labels), inv_t)
+    pm = None
+    if pair:
+        pm = torch.rand(Q, C, generator=g) < 0.2
+        pm[torch.arange(Q), labels] = False
     qr, cr = q.clone().requires_grad_(True), c.clone().requires_grad_(True)
-    loss_r, logits_r = otask.in_batch_loss(qr, cr, mask, labels, 1.0 / inv_t)
-    fin = torch.isfinite(logits_r)
-    assert torch.equal(torch.isfinite(logits.cpu()), fin)
-    _close("score_logits", torch.where(fin, logits.cpu(), torch.zeros(())), torch.where(fin, logits_r, torch.zeros(())), 1e-5, 1e-3, res)
-    _close("score_lse", lse, torch.logsumexp(logits_r, 1), 1e-5, 1e-3, res)
-    got_loss = float(loss_sum) / Q
-    res["loss_abs_err"] = abs(got_loss - float(loss_r))
-    assert res["loss_abs_err"] <= 1e-4 * max(1.0, abs(float(loss_r))), res
-    dq, dc = ops.score_ce_bwd(d_(q), d_(c), logits, d_(labels), lse, 1.0, inv_t, q0, nq, c0, nc)
+    full_mask = mask.unsqueeze(0).expand(Q, -1) if pm is None else (pm | mask.unsqueeze(0))
+    logits_r = otask.sim_score(qr, cr, full_mask) * inv_t
+    loss_r = torch.nn.functional.cross_entropy(logits_r, labels)
     loss_r.backward()
-    _close("score_dq", dq, qr.grad[q0:q0 + nq], 1e-4, 1e-6, res)
-    _close("score_dc", dc, cr.grad[c0:c0 + nc], 1e-4, 1e-6, res)
+    fin = torch.isfinite(logits_r)
+    pmd = None if pm is None else d_(pm.to(torch.uint8))
+
+    def compare(tag, loss_sum, lse, logits, dq, dc):
+        if logits is not None:
+            assert torch.equal(torch.isfinite(logits.cpu()), fin)
+            _close(tag + "logits", torch.where(fin, logits.cpu(), torch.zeros(())), torch.where(fin, logits_r.detach(), torch.zeros(())), 1e-5, 1e-3, res)
+        _close(tag + "lse", lse, torch.logsumexp(logits_r.detach(), 1), 1e-5, 1e-3, res)
+        res[tag + "loss_abs_err"] = abs(float(loss_sum) / Q - float(loss_r))
+        assert res[tag + "loss_abs_err"] <= 1e-4 * max(1.0, abs(float(loss_r))), res
+        _close(tag + "dq", dq, qr.grad[q0:q0 + nq], 1e-4, 1e-6, res)
+        _close(tag + "dc", dc, cr.grad[c0:c0 + nc], 1e-4, 1e-6, res)
+
+    # legacy fp32 FFMA kernels (stored logits)
+    loss_sum, lse, logits = ops.score_ce_fwd_legacy(d_(q), d_(c), d_(mask.to(torch.uint8)), d_(labels), inv_t, True, pmd)
+    dq, dc = ops.score_ce_bwd(d_(q), d_(c), logits, d_(labels), lse, 1.0, inv_t, q0, nq, c0, nc)
+    compare("ffma_", loss_sum, lse, logits, dq, dc)
+    if ops.score_tc_supported(Q, C, d):
+        # training form: no logits, backward recomputes the local tiles
+        loss_sum, lse, logits, ctx = ops.score_fwd(d_(q), d_(c), d_(mask.to(torch.uint8)), d_(labels), inv_t, False, pmd, (nq, nc))
+        assert logits is None and ctx is not None
+        dq, dc = ops.score_bwd(ctx, 1.0, inv_t, q0, nq, c0, nc)
+        compare("tc_", loss_sum, lse, None, dq, dc)
+        # evaluation form: logits requested; a second call on the same shapes (counters must have been reset)
+        loss_sum2, lse2, logits2, _ = ops.score_fwd(d_(q), d_(c), d_(mask.to(torch.uint8)), d_(labels), inv_t, True, pmd)
+        compare("tc2_", loss_sum2, lse2, logits2, dq, dc)
+        assert torch.equal(lse2, lse)
     return res
 
 
@@ -288,6 +312,9 @@ CHECKS = {
 # tcgen05 attention (S <= 128) extra shapes: many problems (persistent loop, barrier phases), heads=12
 CHECKS["score_ce_8gpu_shape"] = lambda: check_score_ce(Q=1024, C=8192, d=768, inv_t=0.125, q0=256, nq=128, c0=2048,
                                                        nc=1024, seed=16)     # cfg 3: global 1024 x 8192 scores per rank
+CHECKS["score_ce_pair_mask"] = lambda: check_score_ce(Q=130, C=300, d=128, inv_t=1.0, q0=1, nq=129, c0=0, nc=300, seed=17, pair=True)
+CHECKS["score_ce_cfg4_shape"] = lambda: check_score_ce(Q=512, C=1024, d=1024, inv_t=1.0, q0=64, nq=64, c0=0, nc=1024, seed=18)
+CHECKS["score_ce_odd_d"] = lambda: check_score_ce(Q=9, C=33, d=100, inv_t=1.0, q0=0, nq=9, c0=0, nc=33, seed=19)   # d % 8 != 0 -> FFMA only
 CHECKS["score_ce_ragged_splits"] = lambda: check_score_ce(Q=70, C=1999, d=200, inv_t=0.5, q0=3, nq=60, c0=17, nc=1500,
                                                           seed=17)
 CHECKS["attn_tc_many"] = lambda: check_attention(40, 128, 12, True, seed=9)

@@ -28,7 +28,12 @@ for Q, C, nq, nc in ((128, 1024, 128, 1024), (1024, 8192, 128, 1024)):
     q, c = torch.randn(Q, d, device="cuda"), torch.randn(C, d, device="cuda")
     mask = torch.zeros(C, dtype=torch.uint8, device="cuda")
     labels = torch.randint(0, C, (Q,), device="cuda")
-    loss, lse, logits = ops.score_ce_fwd(q, c, mask, labels, 1.0)
-    f = timeit(lambda: ops.score_ce_fwd(q, c, mask, labels, 1.0))
+    loss, lse, logits = ops.score_ce_fwd_legacy(q, c, mask, labels, 1.0)
+    f = timeit(lambda: ops.score_ce_fwd_legacy(q, c, mask, labels, 1.0))
     b = timeit(lambda: ops.score_ce_bwd(q, c, logits, labels, lse, 1.0, 1.0, 0, nq, 0, nc))
-    print(f"Q={Q} C={C}: fwd {f:8.1f} us ({2.0*Q*C*d/f/1e6:6.2f} TFLOP/s)   bwd(dq {nq} rows, dc {nc} cols) {b:8.1f} us", flush=True)
+    print(f"Q={Q} C={C} FFMA (r1): fwd {f:8.1f} us ({2.0*Q*C*d/f/1e6:6.2f} TFLOP/s)   bwd(dq {nq} rows, dc {nc} cols) {b:8.1f} us", flush=True)
+    _, _, _, ctx = ops.score_fwd(q, c, mask, labels, 1.0, False, None, (nq, nc))
+    f = timeit(lambda: ops.score_fwd(q, c, mask, labels, 1.0, False, None, (nq, nc)))
+    b = timeit(lambda: ops.score_bwd(ctx, 1.0, 1.0, 0, nq, 0, nc))
+    print(f"Q={Q} C={C} tcgen05 single pass (bf16 x3 split, 6 products): fwd {f:8.1f} us ({2.0*Q*C*d/f/1e6:6.2f} TFLOP/s of fp32-equivalent "
+          f"work, {12.0*Q*C*d/f/1e6:6.1f} executed)   bwd(recompute W + 6 GEMMs) {b:8.1f} us", flush=True)

@@ -55,13 +55,14 @@ SIGNATURES = {
     "dprb_gemm_profile_enable": (c_int, [c_int, c_int]),
     "dprb_gemm_profile_read": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int64)]),
     "dprb_embed_ln_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
-                                  c_float, c_float, c_uint64, _P]),
+                                  c_float, c_float, c_uint64, _P, _P]),
     "dprb_embed_ln_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_float,
                                   c_uint64, _P]),
     "dprb_dropout_site_seed": (c_uint64, [c_uint64, c_int, c_int]),
     "dprb_dropout_mask": (c_int, [_P, c_int64, c_int, c_float, c_uint64, c_int, c_int, _P]),
-    "dprb_ln_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P]),
-    "dprb_ln_bwd": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P, c_float, c_uint64, _P]),
+    "dprb_ln_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_int, _P, _P]),
+    "dprb_ln_bwd": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P, c_float, c_uint64, c_int,
+                            _P]),
     "dprb_colsum_bf16": (c_int, [_P, c_int64, _P, c_int, c_int, _P]),
     "dprb_attn_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_float, c_uint64, _P]),
     "dprb_attn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_uint64, _P]),

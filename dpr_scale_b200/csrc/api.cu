@@ -62,9 +62,9 @@ int dprb_gemm_profile_read(double* total_ms, double* total_flops, int64_t* launc
 int dprb_embed_ln_fwd(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, const float* word,
                       const float* pos, const float* type, const float* gamma, const float* beta, void* y,
                       float* stats, int T, int H, int vocab, int max_pos, int type_vocab, float eps,
-                      float dropout_p, uint64_t dropout_seed, dprb_stream_t stream) {
+                      float dropout_p, uint64_t dropout_seed, void* y_res, dprb_stream_t stream) {
   return embed_ln_fwd(ids, type_ids, pos_ids, word, pos, type, gamma, beta, y, stats, T, H, vocab, max_pos,
-                      type_vocab, eps, dropout_p, dropout_seed, S(stream));
+                      type_vocab, eps, dropout_p, dropout_seed, y_res, S(stream));
 }
 int dprb_embed_ln_bwd(const void* dy, const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids,
                       const float* word, const float* pos, const float* type, const float* gamma,
@@ -74,14 +74,14 @@ int dprb_embed_ln_bwd(const void* dy, const int64_t* ids, const int64_t* type_id
                       dbeta, T, H, dropout_p, dropout_seed, S(stream));
 }
 int dprb_ln_fwd(const void* z, const float* gamma, const float* beta, void* y, float* stats, float* cls_out,
-                int cls_stride, int T, int H, float eps, dprb_stream_t stream) {
-  return ln_fwd(z, gamma, beta, y, stats, cls_out, cls_stride, T, H, eps, S(stream));
+                int cls_stride, int T, int H, float eps, int z_f16, void* y_res, dprb_stream_t stream) {
+  return ln_fwd(z, gamma, beta, y, stats, cls_out, cls_stride, T, H, eps, z_f16, y_res, S(stream));
 }
 int dprb_ln_bwd(const void* dy, const float* dy_cls, int cls_stride, const void* z, const float* stats,
                 const float* gamma, void* dz, float* dgamma, float* dbeta, float* dbias, int T, int H, void* dzm,
-                float dropout_p, uint64_t dropout_site_seed, dprb_stream_t stream) {
+                float dropout_p, uint64_t dropout_site_seed, int z_f16, dprb_stream_t stream) {
   return ln_bwd(dy, dy_cls, cls_stride, z, stats, gamma, dz, dgamma, dbeta, dbias, T, H, dzm, dropout_p,
-                dropout_site_seed, S(stream));
+                dropout_site_seed, z_f16, S(stream));
 }
 uint64_t dprb_dropout_site_seed(uint64_t dropout_seed, int layer, int site) {
   return drop_site_seed64(dropout_seed, layer, site);

@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #ifndef DPRB_HANG_GUARD
@@ -69,6 +70,21 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(t);
 }
+
+// fp16 twins: the encoder keeps its RESIDUAL STREAM (LayerNorm inputs and outputs) in fp16 - 11 significand bits
+// instead of bf16's 8 at the same 2 bytes - because those tensors are re-read by every residual add and their rounding
+// error accumulates over 2L LayerNorms (measured at BERT-base: embedding rel-L2 1.1e-2 with a bf16 stream, 5.2e-3 with
+// fp16; the reference's own bf16 autocast: 6.5e-3).  They are O(1..100) by construction, far from fp16's range limits.
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 t = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t u) {
+  __half2 t = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(t);
+}
+__device__ __forceinline__ uint32_t pack_16x2(float lo, float hi, bool f16) { return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+__device__ __forceinline__ float2 unpack_16x2(uint32_t u, bool f16) { return f16 ? unpack_f16x2(u) : unpack_bf16x2(u); }
 
 // erf-GELU (HF "gelu", modeling_bert.py BertIntermediate) through a fitted Gaussian CDF:
 // Phi(x) = sigma(z(x)), z = a0 x + a1 x^3 + a2 x^5 (least-squares fit on [-6,6], argument clamped to [-8,8]):
@@ -280,6 +296,16 @@ __device__ __forceinline__ uint64_t make_umma_desc_sw128(uint32_t smem_addr, uin
   return d;
 }
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, dense.
+// a_f16 / b_f16: that operand holds IEEE fp16 instead of bf16 (format code 0 instead of 1); the two may differ.
+__host__ __device__ constexpr uint32_t make_idesc_16_f32(int M, int N, int a_mn_major, int b_mn_major, int a_f16, int b_f16) {
+  return (1u << 4)                               // c_format = F32
+         | ((a_f16 ? 0u : 1u) << 7)              // a_format: 0 = F16, 1 = BF16
+         | ((b_f16 ? 0u : 1u) << 10)             // b_format
+         | ((uint32_t)a_mn_major << 15)          // a_major (0 = K, 1 = MN)
+         | ((uint32_t)b_mn_major << 16)          // b_major
+         | ((uint32_t)(N >> 3) << 17)            // n_dim
+         | ((uint32_t)(M >> 4) << 24);           // m_dim
+}
 __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4)                       // c_format = F32
          | (1u << 7)                     // a_format = BF16

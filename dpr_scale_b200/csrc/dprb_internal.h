@@ -16,16 +16,16 @@ int gemm_profile_read(double* total_ms, double* total_flops, long long* launches
 int embed_ln_fwd(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, const float* word,
                  const float* pos, const float* type, const float* gamma, const float* beta, void* y, float* stats,
                  int T, int H, int vocab, int max_pos, int type_vocab, float eps, float dropout_p,
-                 unsigned long long seed, cudaStream_t stream);
+                 unsigned long long seed, void* y_res, cudaStream_t stream);
 int embed_ln_bwd(const void* dy, const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids,
                  const float* word, const float* pos, const float* type, const float* gamma, const float* stats,
                  float* dword, float* dpos, float* dtype, float* dgamma, float* dbeta, int T, int H,
                  float dropout_p, unsigned long long seed, cudaStream_t stream);
 int ln_fwd(const void* z, const float* gamma, const float* beta, void* y, float* stats, float* cls_out,
-           int cls_stride, int T, int H, float eps, cudaStream_t stream);
+           int cls_stride, int T, int H, float eps, int z_f16, void* y_res, cudaStream_t stream);
 int ln_bwd(const void* dy, const float* dy_cls, int cls_stride, const void* z, const float* stats,
            const float* gamma, void* dz, float* dgamma, float* dbeta, float* dbias, int T, int H, void* dzm,
-           float dropout_p, unsigned long long site_seed, cudaStream_t stream);
+           float dropout_p, unsigned long long site_seed, int z_f16, cudaStream_t stream);
 int dropout_mask(uint8_t* out, long long rows, int cols, float p, unsigned long long seed, int layer, int site,
                  cudaStream_t stream);
 unsigned long long drop_site_seed(unsigned long long seed, int layer, int site);

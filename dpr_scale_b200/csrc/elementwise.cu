@@ -26,6 +26,20 @@ __device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
   float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
 }
+// 16-bit rows whose format is a runtime choice (bf16, or fp16 for the encoder's residual stream)
+__device__ __forceinline__ void unpack8x(const uint4& q, float (&v)[8], bool f16) {
+  float2 a = unpack_16x2(q.x, f16), b = unpack_16x2(q.y, f16), c = unpack_16x2(q.z, f16), d = unpack_16x2(q.w, f16);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ void load8x(const bf16* p, float (&v)[8], bool f16) {
+  unpack8x(*reinterpret_cast<const uint4*>(p), v, f16);
+}
+__device__ __forceinline__ void store8x(bf16* p, const float (&v)[8], bool f16) {
+  uint4 q;
+  q.x = pack_16x2(v[0], v[1], f16); q.y = pack_16x2(v[2], v[3], f16);
+  q.z = pack_16x2(v[4], v[5], f16); q.w = pack_16x2(v[6], v[7], f16);
+  *reinterpret_cast<uint4*>(p) = q;
+}
 __device__ __forceinline__ void load8f(const float* p, float (&v)[8]) {
   float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -68,8 +82,12 @@ __global__ void __launch_bounds__(THREADS)
 ln_fwd_kernel(const bf16* __restrict__ z, const int64_t* __restrict__ ids, const int64_t* __restrict__ tts,
               const int64_t* __restrict__ pids, const float* __restrict__ word, const float* __restrict__ pos,
               const float* __restrict__ type, const float* __restrict__ gamma, const float* __restrict__ beta,
-              bf16* __restrict__ y, float* __restrict__ stats, float* __restrict__ cls_out, int cls_stride, int T,
-              int H, float eps, Drop drop) {
+              bf16* __restrict__ y, bf16* __restrict__ y_res, float* __restrict__ stats, float* __restrict__ cls_out,
+              int cls_stride, int T, int H, float eps, Drop drop, int z_f16) {
+  // y: bf16 (the next GEMM's A operand, saved for wgrad).  y_res (optional): the same values in fp16 - the copy the
+  // next residual add reads (tcgen05 kind::f16 cannot mix an fp16 operand with bf16 weights, so the stream that must
+  // stay precise travels beside the GEMM operand instead of replacing it).  z_f16: the input sum holds fp16.
+  const bool f16 = z_f16 != 0;
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * WARPS + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * WARPS;
@@ -102,7 +120,7 @@ ln_fwd_kernel(const bf16* __restrict__ z, const int64_t* __restrict__ ids, const
 #pragma unroll
       for (int i = 0; i < MAXC; ++i) {
         const int c = (lane + 32 * i) * 8;
-        if (act[i]) load8(z + (long long)row * H + c, x[i]);
+        if (act[i]) load8x(z + (long long)row * H + c, x[i], f16);
         else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) x[i][j] = 0.f;
@@ -128,6 +146,7 @@ ln_fwd_kernel(const bf16* __restrict__ z, const int64_t* __restrict__ ids, const
           }
         }
         store8(y + (long long)row * H + c, o);
+        if (y_res != nullptr) store8x(y_res + (long long)row * H + c, o, true);
         if (is_cls) store8f(cls_out + (long long)(row / cls_stride) * H + c, o);
       }
     }
@@ -167,8 +186,9 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ dy_cls, int
               const float* __restrict__ type, const float* __restrict__ stats, const float* __restrict__ gamma,
               bf16* __restrict__ dz, float* __restrict__ dword, float* __restrict__ dpos, float* __restrict__ dtype,
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int T, int H,
-              bf16* __restrict__ dzm, Drop drop) {
+              bf16* __restrict__ dzm, Drop drop, int z_f16) {
   extern __shared__ float smem_f[];
+  const bool zf16 = z_f16 != 0;   // the saved pre-LayerNorm sum z holds fp16 (gradients dy / dz stay bf16)
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * WARPS + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * WARPS;
@@ -252,9 +272,9 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ dy_cls, int
 #pragma unroll
           for (int j = 0; j < 8; ++j) x[j] = (w[j] + t8[j]) + p8[j];
         } else if (dense_path) {
-          unpack8(cz[i], x);
+          unpack8x(cz[i], x, zf16);
         } else {
-          load8(z + (long long)row * H + c, x);
+          load8x(z + (long long)row * H + c, x, zf16);
         }
         if (sparse_dy) load8f(dy_cls + (long long)(row / cls_stride) * H + c, d[i]);
         else if (dense_path) unpack8(cdy[i], d[i]);
@@ -384,13 +404,13 @@ static int check_h(int H, const char* who) {
 int embed_ln_fwd(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, const float* word,
                  const float* pos, const float* type, const float* gamma, const float* beta, void* y, float* stats,
                  int T, int H, int vocab, int max_pos, int type_vocab, float eps, float dropout_p,
-                 unsigned long long seed, cudaStream_t stream) {
+                 unsigned long long seed, void* y_res, cudaStream_t stream) {
   const Drop drop = make_drop(dropout_p, seed, 0, DROP_SITE_EMBED);
   if (int rc = check_h(H, "embed_ln_fwd")) return rc;
   if (T == 0) return 0;
   (void)vocab; (void)max_pos; (void)type_vocab;
   const int grid = grid_for_rows(T);
-#define CALL(C) ln_fwd_kernel<C, true><<<grid, THREADS, 0, stream>>>(nullptr, ids, type_ids, pos_ids, word, pos, type, gamma, beta, (bf16*)y, stats, nullptr, 1, T, H, eps, drop)
+#define CALL(C) ln_fwd_kernel<C, true><<<grid, THREADS, 0, stream>>>(nullptr, ids, type_ids, pos_ids, word, pos, type, gamma, beta, (bf16*)y, (bf16*)y_res, stats, nullptr, 1, T, H, eps, drop, 0)
   DISPATCH_MAXC(H, CALL);
 #undef CALL
   DPRB_LAUNCH_CHECK();
@@ -398,12 +418,12 @@ int embed_ln_fwd(const int64_t* ids, const int64_t* type_ids, const int64_t* pos
 }
 
 int ln_fwd(const void* z, const float* gamma, const float* beta, void* y, float* stats, float* cls_out,
-           int cls_stride, int T, int H, float eps, cudaStream_t stream) {
+           int cls_stride, int T, int H, float eps, int z_f16, void* y_res, cudaStream_t stream) {
   if (int rc = check_h(H, "ln_fwd")) return rc;
   if (T == 0) return 0;
   DPRB_REQUIRE(cls_out == nullptr || cls_stride > 0, "ln_fwd: cls_stride must be positive");
   const int grid = grid_for_rows(T);
-#define CALL(C) ln_fwd_kernel<C, false><<<grid, THREADS, 0, stream>>>((const bf16*)z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, gamma, beta, (bf16*)y, stats, cls_out, cls_stride > 0 ? cls_stride : 1, T, H, eps, Drop{0u, 0u, 1.f, 1u})
+#define CALL(C) ln_fwd_kernel<C, false><<<grid, THREADS, 0, stream>>>((const bf16*)z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, gamma, beta, (bf16*)y, (bf16*)y_res, stats, cls_out, cls_stride > 0 ? cls_stride : 1, T, H, eps, Drop{0u, 0u, 1.f, 1u}, z_f16)
   DISPATCH_MAXC(H, CALL);
 #undef CALL
   DPRB_LAUNCH_CHECK();
@@ -412,7 +432,7 @@ int ln_fwd(const void* z, const float* gamma, const float* beta, void* y, float*
 
 int ln_bwd(const void* dy, const float* dy_cls, int cls_stride, const void* z, const float* stats,
            const float* gamma, void* dz, float* dgamma, float* dbeta, float* dbias, int T, int H, void* dzm,
-           float dropout_p, unsigned long long site_seed, cudaStream_t stream) {
+           float dropout_p, unsigned long long site_seed, int z_f16, cudaStream_t stream) {
   const Drop drop = drop_from_site(dropout_p, site_seed);  // the caller passes the derived site seed
   if (!drop.on()) dzm = nullptr;
   if (int rc = check_h(H, "ln_bwd")) return rc;
@@ -432,7 +452,7 @@ int ln_bwd(const void* dy, const float* dy_cls, int cls_stride, const void* z, c
     DPRB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr = true;
   }
-#define CALL(C) ln_bwd_kernel<C, false><<<grid, THREADS, smem, stream>>>((const bf16*)dy, dy_cls, cls_stride > 0 ? cls_stride : 1, (const bf16*)z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stats, gamma, (bf16*)dz, nullptr, nullptr, nullptr, dgamma, dbeta, dbias, T, H, (bf16*)dzm, drop)
+#define CALL(C) ln_bwd_kernel<C, false><<<grid, THREADS, smem, stream>>>((const bf16*)dy, dy_cls, cls_stride > 0 ? cls_stride : 1, (const bf16*)z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stats, gamma, (bf16*)dz, nullptr, nullptr, nullptr, dgamma, dbeta, dbias, T, H, (bf16*)dzm, drop, z_f16)
   DISPATCH_MAXC(H, CALL);
 #undef CALL
   DPRB_LAUNCH_CHECK();
@@ -448,7 +468,7 @@ int embed_ln_bwd(const void* dy, const int64_t* ids, const int64_t* type_ids, co
   if (T == 0) return 0;
   const int grid = grid_for_rows(T);
   const size_t smem = (size_t)WARPS * H * sizeof(float);
-#define CALL(C) ln_bwd_kernel<C, true><<<grid, THREADS, smem, stream>>>((const bf16*)dy, nullptr, 1, nullptr, ids, type_ids, pos_ids, word, pos, type, stats, gamma, nullptr, dword, dpos, dtype, dgamma, dbeta, nullptr, T, H, nullptr, drop)
+#define CALL(C) ln_bwd_kernel<C, true><<<grid, THREADS, smem, stream>>>((const bf16*)dy, nullptr, 1, nullptr, ids, type_ids, pos_ids, word, pos, type, stats, gamma, nullptr, dword, dpos, dtype, dgamma, dbeta, nullptr, T, H, nullptr, drop, 0)
   DISPATCH_MAXC(H, CALL);
 #undef CALL
   DPRB_LAUNCH_CHECK();

@@ -29,6 +29,7 @@ struct LayerActs {
 };
 
 struct Workspace {
+  bf16 *rA, *rB;   // fp16 residual-stream copies of the LayerNorm outputs (forward only, not saved)
   bf16* x0;
   float* emb_stats;
   int n_layer_slots;
@@ -44,6 +45,8 @@ int plan(const dprb_encoder_weights* w, int nseq, int S, int save, void* base, W
   DPRB_REQUIRE(w->heads * 64 == w->hidden, "encoder: head_dim must be 64 (H=%d heads=%d)", w->hidden, w->heads);
   const long long T = (long long)nseq * S, H = w->hidden, I = w->inter;
   Carve c(base);
+  ws->rA = (bf16*)c.take(T * H * 2);
+  ws->rB = (bf16*)c.take(T * H * 2);
   ws->x0 = (bf16*)c.take(T * H * 2);
   ws->emb_stats = (float*)c.take(T * 2 * 4);
   ws->n_layer_slots = save ? w->layers : 2;
@@ -112,6 +115,13 @@ bool prune_last_layer() {
 
 #define TRY(expr) do { if (int _rc = (expr)) return _rc; } while (0)
 
+// The residual stream travels in fp16: the pre-LayerNorm sums z1 / z2 (saved, read again by the LayerNorm backward) and a
+// transient fp16 copy of every LayerNorm output that the next residual add reads (rA: layer input / output, rB: x1).
+// The bf16 copies of the LayerNorm outputs (x0, x1, out) remain the GEMM operands and what wgrad reads; everything else
+// 16-bit (qkv, ctx, GELU tensors, all gradients) is bf16.  See common.cuh for the measured effect.
+constexpr int RS_F16 = 1;
+constexpr int X16 = DPRB_GEMM_AUX_F16, O16 = DPRB_GEMM_OUT_F16;
+
 }  // namespace
 
 long long encoder_workspace_bytes(const dprb_encoder_weights* w, int nseq, int S, int save) {
@@ -131,7 +141,7 @@ int encoder_fwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b, floa
   const float* ms = w->master;
   TRY(embed_ln_fwd(b->ids, b->type_ids, b->pos_ids, ms + w->off_word, ms + w->off_pos, ms + w->off_type,
                    ms + w->off_emb_ln_g, ms + w->off_emb_ln_b, ws.x0, ws.emb_stats, T, H, w->vocab, w->max_pos,
-                   w->type_vocab, w->ln_eps, b->dropout_p, b->dropout_seed, stream));
+                   w->type_vocab, w->ln_eps, b->dropout_p, b->dropout_seed, ws.rA, stream));
   const bf16* x = ws.x0;
   const float dp = b->dropout_p;
   DPRB_REQUIRE(dp >= 0.f && dp < 1.f, "encoder_fwd: dropout_p %f out of range", dp);
@@ -143,24 +153,24 @@ int encoder_fwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b, floa
       // tokens, everything after the attention scores only for the nseq CLS rows (stored in the first nseq rows of
       // this layer's activation buffers; the saved probabilities reuse the lse buffer).
       const int R = b->nseq;
-      TRY(gemm_bf16(x, lw.wqkv, a.qkv, T, 3 * H, H, H, H, 3 * H, 0, 0, DPRB_EPI_BIAS, lw.bqkv, nullptr, 0, nullptr, 1.f, 1, nullptr, 0.f, 0, stream));
+      TRY(gemm_bf16(x, lw.wqkv, a.qkv, T, 3 * H, H, H, H, 3 * H, 0, 0, DPRB_EPI_BIAS , lw.bqkv, nullptr, 0, nullptr, 1.f, 1, nullptr, 0.f, 0, stream));
       TRY(attn_cls_fwd(a.qkv, b->attn_mask, a.ctx, a.lse, b->nseq, b->S, w->heads, dp, site_seed(b, l, DROP_SITE_ATTN), stream));
-      TRY(gemm_bf16(a.ctx, lw.wo, a.z1, R, H, H, H, H, H, 0, 0, DPRB_EPI_BIAS_RESIDUAL, lw.bo, x, (long long)b->S * H, nullptr, 1.f, 1, nullptr, dp, site_seed_cls(b, l, DROP_SITE_ATTN_OUT), stream));
-      TRY(ln_fwd(a.z1, lw.ln1g, lw.ln1b, a.x1, a.stats1, nullptr, 1, R, H, w->ln_eps, stream));
-      TRY(gemm_bf16(a.x1, lw.w1, a.hact, R, I, H, H, H, I, 0, 0, DPRB_EPI_BIAS_GELU, lw.b1, nullptr, 0, a.hpre, 1.f, 1, nullptr, 0.f, 0, stream));
-      TRY(gemm_bf16(a.hact, lw.w2, a.z2, R, H, I, I, I, H, 0, 0, DPRB_EPI_BIAS_RESIDUAL, lw.b2, a.x1, H, nullptr, 1.f, 1, nullptr, dp, site_seed_cls(b, l, DROP_SITE_FFN_OUT), stream));
-      TRY(ln_fwd(a.z2, lw.ln2g, lw.ln2b, a.out, a.stats2, pooled, 1, R, H, w->ln_eps, stream));
+      TRY(gemm_bf16(a.ctx, lw.wo, a.z1, R, H, H, H, H, H, 0, 0, DPRB_EPI_BIAS_RESIDUAL | X16 | O16, lw.bo, ws.rA, (long long)b->S * H, nullptr, 1.f, 1, nullptr, dp, site_seed_cls(b, l, DROP_SITE_ATTN_OUT), stream));
+      TRY(ln_fwd(a.z1, lw.ln1g, lw.ln1b, a.x1, a.stats1, nullptr, 1, R, H, w->ln_eps, RS_F16, ws.rB, stream));
+      TRY(gemm_bf16(a.x1, lw.w1, a.hact, R, I, H, H, H, I, 0, 0, DPRB_EPI_BIAS_GELU , lw.b1, nullptr, 0, a.hpre, 1.f, 1, nullptr, 0.f, 0, stream));
+      TRY(gemm_bf16(a.hact, lw.w2, a.z2, R, H, I, I, I, H, 0, 0, DPRB_EPI_BIAS_RESIDUAL | X16 | O16, lw.b2, ws.rB, H, nullptr, 1.f, 1, nullptr, dp, site_seed_cls(b, l, DROP_SITE_FFN_OUT), stream));
+      TRY(ln_fwd(a.z2, lw.ln2g, lw.ln2b, a.out, a.stats2, pooled, 1, R, H, w->ln_eps, RS_F16, nullptr, stream));
       x = a.out;
       continue;
     }
-    TRY(gemm_bf16(x, lw.wqkv, a.qkv, T, 3 * H, H, H, H, 3 * H, 0, 0, DPRB_EPI_BIAS, lw.bqkv, nullptr, 0, nullptr, 1.f, 1, nullptr, 0.f, 0, stream));
+    TRY(gemm_bf16(x, lw.wqkv, a.qkv, T, 3 * H, H, H, H, 3 * H, 0, 0, DPRB_EPI_BIAS , lw.bqkv, nullptr, 0, nullptr, 1.f, 1, nullptr, 0.f, 0, stream));
     TRY(attn_fwd_lse(a.qkv, b->attn_mask, a.ctx, a.lse, b->nseq, b->S, w->heads, dp, site_seed(b, l, DROP_SITE_ATTN), stream));
-    TRY(gemm_bf16(a.ctx, lw.wo, a.z1, T, H, H, H, H, H, 0, 0, DPRB_EPI_BIAS_RESIDUAL, lw.bo, x, H, nullptr, 1.f, 1, nullptr, dp, site_seed(b, l, DROP_SITE_ATTN_OUT), stream));
-    TRY(ln_fwd(a.z1, lw.ln1g, lw.ln1b, a.x1, a.stats1, nullptr, 1, T, H, w->ln_eps, stream));
-    TRY(gemm_bf16(a.x1, lw.w1, a.hact, T, I, H, H, H, I, 0, 0, DPRB_EPI_BIAS_GELU, lw.b1, nullptr, 0, a.hpre, 1.f, 1, nullptr, 0.f, 0, stream));
-    TRY(gemm_bf16(a.hact, lw.w2, a.z2, T, H, I, I, I, H, 0, 0, DPRB_EPI_BIAS_RESIDUAL, lw.b2, a.x1, H, nullptr, 1.f, 1, nullptr, dp, site_seed(b, l, DROP_SITE_FFN_OUT), stream));
+    TRY(gemm_bf16(a.ctx, lw.wo, a.z1, T, H, H, H, H, H, 0, 0, DPRB_EPI_BIAS_RESIDUAL | X16 | O16, lw.bo, ws.rA, H, nullptr, 1.f, 1, nullptr, dp, site_seed(b, l, DROP_SITE_ATTN_OUT), stream));
+    TRY(ln_fwd(a.z1, lw.ln1g, lw.ln1b, a.x1, a.stats1, nullptr, 1, T, H, w->ln_eps, RS_F16, ws.rB, stream));
+    TRY(gemm_bf16(a.x1, lw.w1, a.hact, T, I, H, H, H, I, 0, 0, DPRB_EPI_BIAS_GELU , lw.b1, nullptr, 0, a.hpre, 1.f, 1, nullptr, 0.f, 0, stream));
+    TRY(gemm_bf16(a.hact, lw.w2, a.z2, T, H, I, I, I, H, 0, 0, DPRB_EPI_BIAS_RESIDUAL | X16 | O16, lw.b2, ws.rB, H, nullptr, 1.f, 1, nullptr, dp, site_seed(b, l, DROP_SITE_FFN_OUT), stream));
     const bool last = (l == L - 1);
-    TRY(ln_fwd(a.z2, lw.ln2g, lw.ln2b, a.out, a.stats2, last ? pooled : nullptr, b->S, T, H, w->ln_eps, stream));
+    TRY(ln_fwd(a.z2, lw.ln2g, lw.ln2b, a.out, a.stats2, last ? pooled : nullptr, b->S, T, H, w->ln_eps, RS_F16, last ? nullptr : ws.rA, stream));
     x = a.out;
   }
   return 0;
@@ -187,13 +197,13 @@ int encoder_bwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b, cons
     if (last && prune_last_layer()) {
       const int R = b->nseq;
       TRY(ln_bwd(nullptr, dpooled, 1, a.z2, a.stats2, lw.ln2g, ws.gB, lw.g_ln2g, lw.g_ln2b, lw.g_b2, R, H, ws.gB2, dp,
-                 site_seed_cls(b, l, DROP_SITE_FFN_OUT), stream));
+                 site_seed_cls(b, l, DROP_SITE_FFN_OUT), RS_F16, stream));
       TRY(gemm_bf16(gLin, a.hact, lw.g_w2, H, I, R, H, I, I, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, 0.f, 0, stream));
       TRY(gemm_bf16(gLin, lw.w2, ws.gH, R, I, H, H, I, I, 0, 1, DPRB_EPI_DGELU, nullptr, a.hpre, I, nullptr, 1.f, 1, lw.g_b1, 0.f, 0, stream));
       TRY(gemm_bf16(ws.gH, a.x1, lw.g_w1, I, H, R, I, H, H, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, 0.f, 0, stream));
       TRY(gemm_bf16(ws.gH, lw.w1, ws.gA, R, H, I, I, H, H, 0, 1, DPRB_EPI_BIAS_RESIDUAL, nullptr, ws.gB, H, nullptr, 1.f, 1, nullptr, 0.f, 0, stream));
       TRY(ln_bwd(ws.gA, nullptr, 1, a.z1, a.stats1, lw.ln1g, ws.gB, lw.g_ln1g, lw.g_ln1b, lw.g_bo, R, H, ws.gB2, dp,
-                 site_seed_cls(b, l, DROP_SITE_ATTN_OUT), stream));
+                 site_seed_cls(b, l, DROP_SITE_ATTN_OUT), RS_F16, stream));
       TRY(gemm_bf16(gLin, a.ctx, lw.g_wo, H, H, R, H, H, H, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, 0.f, 0, stream));
       TRY(gemm_bf16(gLin, lw.wo, ws.gA, R, H, H, H, H, H, 0, 1, DPRB_EPI_BIAS, nullptr, nullptr, 0, nullptr, 1.f, 1, nullptr, 0.f, 0, stream));
       TRY(attn_cls_bwd(a.qkv, a.lse, ws.gA, ws.gQKV, b->nseq, b->S, w->heads, dp, site_seed(b, l, DROP_SITE_ATTN), stream));
@@ -206,7 +216,7 @@ int encoder_bwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b, cons
     }
     // LN2 backward (+ db2)
     TRY(ln_bwd(last ? nullptr : ws.gA, last ? dpooled : nullptr, b->S, a.z2, a.stats2, lw.ln2g, ws.gB, lw.g_ln2g,
-               lw.g_ln2b, lw.g_b2, T, H, ws.gB2, dp, site_seed(b, l, DROP_SITE_FFN_OUT), stream));
+               lw.g_ln2b, lw.g_b2, T, H, ws.gB2, dp, site_seed(b, l, DROP_SITE_FFN_OUT), RS_F16, stream));
     // dW2 += dz2^T hact
     TRY(gemm_bf16(gLin, a.hact, lw.g_w2, H, I, T, H, I, I, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, 0.f, 0, stream));
     // dhpre = (dz2 W2) * gelu'(hpre)
@@ -218,7 +228,7 @@ int encoder_bwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b, cons
     TRY(gemm_bf16(ws.gH, lw.w1, ws.gA, T, H, I, I, H, H, 0, 1, DPRB_EPI_BIAS_RESIDUAL, nullptr, ws.gB, H, nullptr, 1.f, 1, nullptr, 0.f, 0, stream));
     // LN1 backward (+ dbo)
     TRY(ln_bwd(ws.gA, nullptr, 1, a.z1, a.stats1, lw.ln1g, ws.gB, lw.g_ln1g, lw.g_ln1b, lw.g_bo, T, H, ws.gB2, dp,
-               site_seed(b, l, DROP_SITE_ATTN_OUT), stream));
+               site_seed(b, l, DROP_SITE_ATTN_OUT), RS_F16, stream));
     // dWo += dz1^T ctx
     TRY(gemm_bf16(gLin, a.ctx, lw.g_wo, H, H, T, H, H, H, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, 0.f, 0, stream));
     // dctx = dz1 Wo

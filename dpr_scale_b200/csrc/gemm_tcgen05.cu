@@ -66,6 +66,8 @@ struct GemmParams {
   float* colsum;       // optional: colsum[n] += sum_m D(m, n) of the bf16-rounded output (bias gradients)
   int aux_prefetch;    // 1: request aux with cp.async before waiting for the accumulator (CG = 2 only)
   Drop drop;           // EPI_BIAS_RESIDUAL only: D = dropout(acc + bias) + aux  (hidden dropout before the residual)
+  uint32_t idesc;      // UMMA instruction descriptor (operand formats: bf16 or fp16 per operand)
+  int aux_f16, out_f16;  // aux / D hold fp16 instead of bf16 (the encoder's fp16 residual stream)
 };
 
 // ---- cluster / 2-CTA helpers -------------------------------------------------------------------------------
@@ -216,7 +218,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp == 1) {
     // ================================ MMA issuer (one thread of the leader CTA) ================================
     if (lane == 0 && is_leader) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(CTA_M * CG, BLOCK_N, A_MN, B_MN);
+      const uint32_t idesc = p.idesc;
       // K-major SW128: 8-row groups are 1024 B apart (SBO); LBO unused inside one swizzle atom.
       // MN-major SW128: 64-element MN atoms are BLOCK_K*128 B apart (LBO); 8-deep K groups 1024 B apart (SBO).
       constexpr uint32_t A_LBO = A_MN ? BLOCK_K * 128 : 0, A_SBO = 1024;
@@ -457,7 +459,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               for (int c4 = 0; c4 < 4; ++c4) {
                 const int ch = h * 4 + c4;
                 const uint4 q = *reinterpret_cast<const uint4*>(slab + lane * 128 + ((ch ^ (lane & 7)) << 4));
-                const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z), f3 = unpack_bf16x2(q.w);
+                const bool af = p.aux_f16 != 0;
+                const float2 f0 = unpack_16x2(q.x, af), f1 = unpack_16x2(q.y, af), f2 = unpack_16x2(q.z, af), f3 = unpack_16x2(q.w, af);
                 const float a[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
@@ -470,8 +473,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int c4 = 0; c4 < 4; ++c4) {
               const int ch = h * 4 + c4;
               uint4 q;
-              q.x = pack_bf16x2(v[c4 * 8 + 0], v[c4 * 8 + 1]); q.y = pack_bf16x2(v[c4 * 8 + 2], v[c4 * 8 + 3]);
-              q.z = pack_bf16x2(v[c4 * 8 + 4], v[c4 * 8 + 5]); q.w = pack_bf16x2(v[c4 * 8 + 6], v[c4 * 8 + 7]);
+              const bool of = p.out_f16 != 0;
+              q.x = pack_16x2(v[c4 * 8 + 0], v[c4 * 8 + 1], of); q.y = pack_16x2(v[c4 * 8 + 2], v[c4 * 8 + 3], of);
+              q.z = pack_16x2(v[c4 * 8 + 4], v[c4 * 8 + 5], of); q.w = pack_16x2(v[c4 * 8 + 6], v[c4 * 8 + 7], of);
               *reinterpret_cast<uint4*>(slab + lane * 128 + ((ch ^ (lane & 7)) << 4)) = q;
             }
           }
@@ -587,7 +591,16 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long l
               long long ld_aux, void* out2, float alpha, int splits, float* colsum, float dropout_p,
               unsigned long long drop_site_seed, cudaStream_t stream) {
   DPRB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  const int dt_flags = epilogue & ~0xFF;   // DPRB_GEMM_{A,B,AUX,OUT}_F16
+  epilogue &= 0xFF;
+  const int a_f16 = (dt_flags & DPRB_GEMM_A_F16) != 0, b_f16 = (dt_flags & DPRB_GEMM_B_F16) != 0;
+  const int aux_f16 = (dt_flags & DPRB_GEMM_AUX_F16) != 0, out_f16 = (dt_flags & DPRB_GEMM_OUT_F16) != 0;
   DPRB_REQUIRE(epilogue >= 0 && epilogue < DPRB_EPI_COUNT, "gemm: bad epilogue %d", epilogue);
+  DPRB_REQUIRE(!(aux_f16 || out_f16) || epilogue == DPRB_EPI_BIAS || epilogue == DPRB_EPI_BIAS_RESIDUAL,
+               "gemm: fp16 aux / output is implemented for the BIAS and BIAS_RESIDUAL epilogues only");
+  DPRB_REQUIRE(a_f16 == b_f16, "gemm: tcgen05 kind::f16 rejects an fp16 x bf16 operand pair (illegal instruction): give "
+               "DPRB_GEMM_A_F16 and DPRB_GEMM_B_F16 together or not at all");
+  DPRB_REQUIRE(!out_f16 || colsum == nullptr, "gemm: colsum reads a bf16 slab (not available with fp16 output)");
   const bool f32_out = (epilogue == DPRB_EPI_F32_ATOMIC_ADD || epilogue == DPRB_EPI_F32_STORE);
   DPRB_REQUIRE(f32_out || (ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0),
                "gemm: bf16 output must be 16-byte aligned with ldd %% 8 == 0 (ldd=%lld)", ldd);
@@ -637,6 +650,8 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long l
   p.D = D; p.ldd = ldd; p.bias = bias; p.aux = reinterpret_cast<const bf16*>(aux); p.ld_aux = ld_aux;
   p.out2 = reinterpret_cast<bf16*>(out2); p.alpha = alpha;
   p.colsum = colsum;
+  p.aux_f16 = aux_f16; p.out_f16 = out_f16;
+  p.idesc = make_idesc_16_f32(CTA_M * CG, BLOCK_N, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, a_f16, b_f16);
   p.drop = drop_from_site(epilogue == DPRB_EPI_BIAS_RESIDUAL ? dropout_p : 0.f, drop_site_seed);
   static const bool no_aux_pf = (std::getenv("DPRB_NO_AUX_PF") != nullptr);
   // measured (same box, cfg-2 shapes): prefetching aux before the accumulator wait gains 10-14 % where the epilogue

@@ -5,10 +5,13 @@
 // Replaces /root/reference/dpr_scale/task/dpr_task.py:98-105 (sim_score), :197 / :199-207 (masks), :211 (/= T),
 // :212 (nn.CrossEntropyLoss) and, in backward, the gradient flow of :163-195 (only rank-local rows / columns).
 //
-// fp32 fidelity on bf16 tensor cores: every fp32 operand x is split EXACTLY into three bf16 parts x = h + m + l
-// (|residual| <= 2^-27 |x|), and the product is accumulated in fp32 from the six partial products whose magnitude is
-// above 2^-27: hl, lh, mm, hm, mh, hh.  Measured against the fp64 product the logits agree to ~1e-6 relative - inside
-// the 1e-5 gate of SURVEY 8(c) - where the reference under AMP computes this product in fp16 (spacing 0.25 at |s| ~ 300).
+// fp32 fidelity on bf16 tensor cores ("bf16x3"): every fp32 operand x is split into two bf16 parts x ~ h + m
+// (|x - h - m| <= 2^-18 |x|), and q.c is accumulated in fp32 from the three partial products h.m, m.h, h.h (the dropped
+// m.m term is 2^-18 of the product).  Each term of the dot product is therefore exact to ~2^-17; measured against the
+// fp64 product the logits agree to a few 1e-6 of max|logit| - inside the 1e-5 |logit| + 1e-3 gate of SURVEY 8(c) -
+// where the reference under AMP computes this product in fp16 (spacing 0.25 at |s| ~ 300).  (A three-part split with
+// six products was measured first: 1.5x the L2 -> shared-memory traffic, which is what bounds this kernel, for
+// accuracy nobody can observe behind the fp32 softmax.)
 //
 // Backward recomputes tiles instead of reading stored logits: one launch rebuilds W = softmax - onehot for the local
 // row block [nq x C] and the local column block [Q x nc] (bf16 hi + lo), and dq = W_rows c, dc = W_cols^T q run as
@@ -21,8 +24,8 @@ namespace {
 
 constexpr int TM = 128, TN = 128, BK = 64;
 constexpr int PART_BYTES = 128 * 128;          // [128 rows][64 bf16], 128B-swizzled
-constexpr int STAGE_BYTES = 6 * PART_BYTES;    // q.h q.m q.l c.h c.m c.l of one k-block
-constexpr int STAGES = 2;
+constexpr int STAGE_BYTES = 4 * PART_BYTES;    // q.h q.m c.h c.m of one k-block
+constexpr int STAGES = 3;
 constexpr int EPI_THREADS = 128;
 constexpr int THREADS = 128 + EPI_THREADS;     // warps 0..3: TMA, MMA, TMEM alloc, spare; warps 4..7: epilogue
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * 128 * 4 + 256 + 1024;
@@ -62,28 +65,24 @@ __device__ __forceinline__ float lg2_approx(float x) {
   return y;
 }
 
-// exact three-way bf16 split of fp32 data: out[0] = h, out[1] = m, out[2] = l  (part stride n elements)
+// two-way bf16 split of fp32 data: out[0] = h = bf16(x), out[1] = m = bf16(x - h)  (part stride n elements)
 __global__ void __launch_bounds__(256)
-split3_kernel(const float* __restrict__ x, bf16* __restrict__ out, long long n) {
+split2_kernel(const float* __restrict__ x, bf16* __restrict__ out, long long n) {
   const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(x)[i];
     const float a[4] = {v.x, v.y, v.z, v.w};
-    float h[4], m[4], l[4];
+    float h[4], m[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       h[t] = __bfloat162float(__float2bfloat16_rn(a[t]));
-      const float r1 = a[t] - h[t];
-      m[t] = __bfloat162float(__float2bfloat16_rn(r1));
-      l[t] = r1 - m[t];
+      m[t] = a[t] - h[t];
     }
     uint2 s;
     s.x = pack_bf16x2(h[0], h[1]); s.y = pack_bf16x2(h[2], h[3]);
     reinterpret_cast<uint2*>(out)[i] = s;
     s.x = pack_bf16x2(m[0], m[1]); s.y = pack_bf16x2(m[2], m[3]);
     reinterpret_cast<uint2*>(out + n)[i] = s;
-    s.x = pack_bf16x2(l[0], l[1]); s.y = pack_bf16x2(l[2], l[3]);
-    reinterpret_cast<uint2*>(out + 2 * n)[i] = s;
   }
 }
 
@@ -130,9 +129,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
           uint8_t* base = smem + stage * STAGE_BYTES;
 #pragma unroll
-          for (int part = 0; part < 3; ++part) {
+          for (int part = 0; part < 2; ++part) {
             tma_load_3d(base + part * PART_BYTES, &tm_q, &full_bar[stage], kb * BK, row0, part);
-            tma_load_3d(base + (3 + part) * PART_BYTES, &tm_c, &full_bar[stage], kb * BK, col0, part);
+            tma_load_3d(base + (2 + part) * PART_BYTES, &tm_c, &full_bar[stage], kb * BK, col0, part);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -152,13 +151,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t base = smem_u32(smem + stage * STAGE_BYTES);
-          // smallest partial products first: (h,l) (l,h) (m,m) (h,m) (m,h) (h,h)
-          constexpr int PA[6] = {0, 2, 1, 0, 1, 0};
-          constexpr int PB[6] = {2, 0, 1, 1, 0, 0};
+          // small partial products first: (h,m) (m,h) (h,h)
+          constexpr int PA[3] = {0, 1, 0};
+          constexpr int PB[3] = {1, 0, 0};
 #pragma unroll
-          for (int pr = 0; pr < 6; ++pr) {
+          for (int pr = 0; pr < 3; ++pr) {
             const uint64_t da = make_umma_desc_sw128(base + PA[pr] * PART_BYTES, 0, 1024);
-            const uint64_t db = make_umma_desc_sw128(base + (3 + PB[pr]) * PART_BYTES, 0, 1024);
+            const uint64_t db = make_umma_desc_sw128(base + (2 + PB[pr]) * PART_BYTES, 0, 1024);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || pr > 0 || k > 0) ? 1u : 0u);
           }
@@ -354,11 +353,11 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// bf16 [3 parts][rows][d]; box = [1][128 rows][64 cols], 128B swizzle; rows / columns beyond the extent are zero-filled
+// bf16 [2 parts][rows][d]; box = [1][128 rows][64 cols], 128B swizzle; rows / columns beyond the extent are zero-filled
 int make_tmap_parts(CUtensorMap* out, const void* base, long long rows, long long d) {
   EncodeTiledFn fn = encode_fn();
   DPRB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
-  cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)rows, 3};
+  cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)rows, 2};
   cuuint64_t strides[2] = {(cuuint64_t)d * 2, (cuuint64_t)rows * d * 2};
   cuuint32_t box[3] = {64u, 128u, 1u};
   cuuint32_t estr[3] = {1u, 1u, 1u};
@@ -387,8 +386,8 @@ ScoreWs plan(void* base, int Q, int C, int d, int nq, int nc) {
   long long off = 0;
   auto take = [&](long long bytes) { uint8_t* ptr = b ? b + off : nullptr; off += al256(bytes); return ptr; };
   w.n_rb = (Q + TM - 1) / TM; w.n_cb = (C + TN - 1) / TN; w.Qpad = w.n_rb * TM;
-  w.q3 = (bf16*)take(3LL * Q * d * 2);
-  w.c3 = (bf16*)take(3LL * C * d * 2);
+  w.q3 = (bf16*)take(2LL * Q * d * 2);
+  w.c3 = (bf16*)take(2LL * C * d * 2);
   w.part = (float*)take(3LL * w.n_cb * w.Qpad * 4);
   w.counters = (int*)take((long long)w.n_rb * 4);
   w.ld_wr = (C + 7) & ~7LL; w.ld_wc = ((long long)nc + 7) & ~7LL;
@@ -437,9 +436,9 @@ int score_tc_fwd(const float* q, const float* c, const uint8_t* col_mask, const 
                "score_tc_fwd: workspace missing, misaligned or too small (%lld < %lld)", workspace_bytes, w.bytes);
   if (int rc = set_attr()) return rc;
   const long long nqd = (long long)Q * d, ncd = (long long)C * d;
-  split3_kernel<<<grid_for(nqd >> 2), 256, 0, stream>>>(q, w.q3, nqd);
+  split2_kernel<<<grid_for(nqd >> 2), 256, 0, stream>>>(q, w.q3, nqd);
   DPRB_LAUNCH_CHECK();
-  split3_kernel<<<grid_for(ncd >> 2), 256, 0, stream>>>(c, w.c3, ncd);
+  split2_kernel<<<grid_for(ncd >> 2), 256, 0, stream>>>(c, w.c3, ncd);
   DPRB_LAUNCH_CHECK();
   DPRB_CHECK_CUDA(cudaMemsetAsync(w.counters, 0, (size_t)w.n_rb * 4, stream));
   CUtensorMap tq, tc;

@@ -60,6 +60,8 @@ struct SearchParams {
   int m_track;          // m = ceil(k / partitions) if <= 8, else 0 (cross-partition bound disabled)
   int pf_ahead;         // corpus k-block boxes prefetched into L2 ahead of the shared-memory ring (0 = off)
   uint32_t idesc;
+  int rank_f16;         // rank by the fp16-ROUNDED score: the reference's einsum on fp16 tensors returns fp16
+                        // (run_retrieval_pytorch.py:150-151), so its topk orders fp16 values; ties go to the lower row id
 };
 
 // TMA prefetch of one box into L2 (no shared-memory destination, no barrier)
@@ -301,10 +303,12 @@ search_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         float cmax = __uint_as_float(r[0]);
 #pragma unroll
         for (int j = 1; j < 32; ++j) cmax = fmaxf(cmax, __uint_as_float(r[j]));
+        if (p.rank_f16) cmax = __half2float(__float2half_rn(cmax));   // rounding is monotone: max commutes with it
         if (cmax >= lowbar) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float v = __uint_as_float(r[j]);
+            float v = __uint_as_float(r[j]);
+            if (p.rank_f16) v = __half2float(__float2half_rn(v));
             if (v >= lowbar && j < nvalid) {
               if (v >= thr) myq[cnt++] = make_key(v, ib + j);
               if (v > t7_) {
@@ -560,6 +564,8 @@ int search_topk(const void* queries, const void* corpus, int dtype, long long Q,
                 long long index_offset, float* out_scores, long long* out_index, void* workspace,
                 long long workspace_bytes, cudaStream_t stream) {
   DPRB_REQUIRE(Q > 0 && N > 0 && d > 0, "search: empty problem Q=%lld N=%lld d=%d", Q, N, d);
+  const int rank_f16 = (dtype & DPRB_SEARCH_RANK_FP16) != 0;
+  dtype &= 0xFF;
   DPRB_REQUIRE(dtype == 0 || dtype == 1, "search: dtype must be 0 (fp16) or 1 (bf16), got %d", dtype);
   DPRB_REQUIRE(k >= 1 && k <= 1024, "search: k=%d outside [1, 1024]", k);
   DPRB_REQUIRE(N >= k, "search: k=%d exceeds the %lld corpus rows (torch.topk raises here too)", k, N);
@@ -604,6 +610,7 @@ int search_topk(const void* queries, const void* corpus, int dtype, long long Q,
     sp.N = N; sp.Q = Qb; sp.d = d; sp.k = k; sp.kblocks = (d + BK - 1) / BK;
     sp.tiles = tiles; sp.tiles_per_part = tpp; sp.queues = queues; sp.counts = counts;
     sp.idesc = make_idesc16(QT, CT, dtype);
+    sp.rank_f16 = rank_f16;
     const long long m = (k + parts - 1) / parts;
     sp.bounds = bounds;
     {

@@ -9,6 +9,8 @@ from . import _lib
 from ._lib import check
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_DGELU, EPI_F32_ATOMIC_ADD, EPI_F32_STORE = range(6)
+# OR-ed into the epilogue: that operand holds fp16 instead of bf16 (include/dprb.h DPRB_GEMM_*_F16)
+GEMM_A_F16, GEMM_B_F16, GEMM_AUX_F16, GEMM_OUT_F16 = 0x100, 0x200, 0x400, 0x800
 
 def launch_count():
     """Kernels launched by libdprb.so in this process so far (counted inside the C launchers)."""
@@ -50,14 +52,15 @@ def linear_fwd(x, w, bias=None, epilogue=EPI_BIAS, aux=None, out2=None):
     return y
 
 
-def embed_ln_fwd(ids, type_ids, pos_ids, word, pos, typ, gamma, beta, eps, dropout_p=0.0, seed=0):
+def embed_ln_fwd(ids, type_ids, pos_ids, word, pos, typ, gamma, beta, eps, dropout_p=0.0, seed=0, y_res=None):
+    """y_res: optional fp16 [T, H] tensor that receives a second copy of the output (the residual-stream copy)."""
     T = ids.numel()
     H = word.shape[1]
     y = torch.empty(T, H, dtype=torch.bfloat16, device=word.device)
     stats = torch.empty(T, 2, dtype=torch.float32, device=word.device)
     check(_lib.load().dprb_embed_ln_fwd(_ptr(ids), _ptr(type_ids), _ptr(pos_ids), _ptr(word), _ptr(pos), _ptr(typ),
                                         _ptr(gamma), _ptr(beta), _ptr(y), _ptr(stats), T, H, word.shape[0],
-                                        pos.shape[0], typ.shape[0], float(eps), float(dropout_p), int(seed),
+                                        pos.shape[0], typ.shape[0], float(eps), float(dropout_p), int(seed), _ptr(y_res),
                                         _stream()), "dprb_embed_ln_fwd")
     _count()
     return y, stats
@@ -74,26 +77,28 @@ def embed_ln_bwd(dy, ids, type_ids, pos_ids, word, pos, typ, gamma, stats, dword
     _count()
 
 
-def ln_fwd(z, gamma, beta, eps, cls_stride=0):
+def ln_fwd(z, gamma, beta, eps, cls_stride=0, y_res=None):
+    """z: bf16, or fp16 (the encoder's residual-stream sums); y: bf16; y_res: optional fp16 copy of y."""
     T, H = z.shape
-    y = torch.empty_like(z)
+    y = torch.empty(T, H, dtype=torch.bfloat16, device=z.device)
     stats = torch.empty(T, 2, dtype=torch.float32, device=z.device)
     cls = None
     if cls_stride:
         cls = torch.empty((T + cls_stride - 1) // cls_stride, H, dtype=torch.float32, device=z.device)
     check(_lib.load().dprb_ln_fwd(_ptr(z), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(stats), _ptr(cls),
-                                  cls_stride if cls_stride else 1, T, H, float(eps), _stream()), "dprb_ln_fwd")
+                                  cls_stride if cls_stride else 1, T, H, float(eps), int(z.dtype == torch.float16),
+                                  _ptr(y_res), _stream()), "dprb_ln_fwd")
     _count()
     return y, stats, cls
 
 
 def ln_bwd(dy, z, stats, gamma, dgamma, dbeta, dbias=None, dy_cls=None, cls_stride=1, dropout_p=0.0, site_seed=0):
     T, H = z.shape
-    dz = torch.empty_like(z)
-    dzm = torch.empty_like(z) if dropout_p > 0 else None
+    dz = torch.empty(z.shape, dtype=torch.bfloat16, device=z.device)      # gradients are bf16 whatever z holds
+    dzm = torch.empty_like(dz) if dropout_p > 0 else None
     check(_lib.load().dprb_ln_bwd(_ptr(dy), _ptr(dy_cls), cls_stride, _ptr(z), _ptr(stats), _ptr(gamma), _ptr(dz),
                                   _ptr(dgamma), _ptr(dbeta), _ptr(dbias), T, H, _ptr(dzm), float(dropout_p),
-                                  int(site_seed), _stream()), "dprb_ln_bwd")
+                                  int(site_seed), int(z.dtype == torch.float16), _stream()), "dprb_ln_bwd")
     _count()
     return (dz, dzm) if dropout_p > 0 else dz
 
@@ -263,9 +268,10 @@ def _search_ws(nbytes, device):
     return buf
 
 
-def search_topk(queries, corpus, k, index_offset=0):
+def search_topk(queries, corpus, k, index_offset=0, reference_ranking=False):
     """Fused inner-product search + top-k: queries [Q, d], corpus [N, d] (both fp16 or both bf16, contiguous)
-    -> (scores fp32 [Q, k] descending, row ids int64 [Q, k]); never materialises the [Q, N] score matrix."""
+    -> (scores fp32 [Q, k] descending, row ids int64 [Q, k]); never materialises the [Q, N] score matrix.
+    reference_ranking: order by the fp16-rounded score, as the reference's topk over its fp16 einsum does."""
     assert queries.dtype == corpus.dtype and queries.dtype in (torch.float16, torch.bfloat16)
     assert queries.is_contiguous() and corpus.is_contiguous() and queries.shape[1] == corpus.shape[1]
     lib = _lib.load()
@@ -274,7 +280,8 @@ def search_topk(queries, corpus, k, index_offset=0):
     ws = _search_ws(lib.dprb_search_workspace_bytes(Q, int(k)), queries.device)
     scores = torch.empty(Q, k, dtype=torch.float32, device=queries.device)
     index = torch.empty(Q, k, dtype=torch.int64, device=queries.device)
-    check(lib.dprb_search_topk(_ptr(queries), _ptr(corpus), 1 if queries.dtype == torch.bfloat16 else 0, Q, N, d,
+    check(lib.dprb_search_topk(_ptr(queries), _ptr(corpus),
+                               (1 if queries.dtype == torch.bfloat16 else 0) | (0x100 if reference_ranking else 0), Q, N, d,
                                int(k), int(index_offset), _ptr(scores), _ptr(index), _ptr(ws), ws.numel(),
                                _stream()), "dprb_search_topk")
     _count(2 * ((Q + 1023) // 1024))

@@ -52,6 +52,10 @@ def get_parser():
     p.add_argument("--ignore_identical_ids", action="store_true",
                    help="this is used for BEIR Arguana and Quora datasets")
     p.add_argument("--fp32_scores", action="store_true", help="write fp32 scores instead of fp16-rounded ones")
+    p.add_argument("--reference_ranking", action="store_true",
+                   help="rank by the fp16-ROUNDED score like the reference's topk over its fp16 einsum "
+                        "(run_retrieval_pytorch.py:150-151): ids equal the reference's wherever its fp16 scores are "
+                        "distinct.  Default: rank by the exact fp32-accumulated score (finer, deterministic order)")
     p.add_argument("--device", type=str, default="cuda", help="device holding the index (the kernels need CUDA)")
     return p
 
@@ -77,21 +81,21 @@ def build_index(paths, device="cuda"):
     return torch.cat(parts, dim=0) if len(parts) > 1 else parts[0].contiguous()
 
 
-def search_index(query_embs, corpus_embs, batch, topk, index_offset=0):
+def search_index(query_embs, corpus_embs, batch, topk, index_offset=0, reference_ranking=False):
     """(scores [Q, k] fp32, row ids [Q, k] int64) on the GPU; argument meaning as run_retrieval_pytorch.py:141."""
     del batch
     q = torch.as_tensor(query_embs).to(device=corpus_embs.device, dtype=corpus_embs.dtype).contiguous()
-    return ops.search_topk(q, corpus_embs, topk, index_offset=index_offset)
+    return ops.search_topk(q, corpus_embs, topk, index_offset=index_offset, reference_ranking=reference_ranking)
 
 
-def search_segments(q_repr, input_paths, shard, batch, topk, device="cuda"):
+def search_segments(q_repr, input_paths, shard, batch, topk, device="cuda", reference_ranking=False):
     """Search ``shard`` sequential index segments and merge (run_retrieval_pytorch.py:204-230, :272-277)."""
     assert len(input_paths) % shard == 0, "Invalid Shard number"
     per = len(input_paths) // shard
     all_s, all_i, offset = [], [], 0
     for seg in range(shard):
         index = build_index(input_paths[seg * per:(seg + 1) * per], device)
-        s, i = search_index(q_repr, index, batch, topk, index_offset=offset)
+        s, i = search_index(q_repr, index, batch, topk, index_offset=offset, reference_ranking=reference_ranking)
         offset += index.shape[0]
         del index
         all_s.append(s)
@@ -137,20 +141,21 @@ def gather_rank_lists(scores, indexes):
     return torch.cat(ss, dim=1).contiguous(), torch.cat(ii, dim=1).contiguous()
 
 
-def search_distributed(q_repr, input_paths, shard, batch, topk, device="cuda"):
+def search_distributed(q_repr, input_paths, shard, batch, topk, device="cuda", reference_ranking=False):
     """Every rank searches its own block of the index (the reps_{rank} files it wrote in generate_embeddings) and
     the W lists are merged with one all-gather + ops.topk_merge; every rank returns the global result.  The only
     data-path collective is that all-gather of [Q, k] scores and ids (no corpus bytes move between GPUs)."""
     world = _world()
     if world == 1:
-        return search_segments(q_repr, input_paths, shard, batch, topk, device)
+        return search_segments(q_repr, input_paths, shard, batch, topk, device, reference_ranking)
     mine = rank_files(input_paths, dist.get_rank(), world)
     assert len(mine) % shard == 0, "Invalid Shard number"
     per = len(mine) // shard
     all_s, all_i, rows = [], [], 0
     for seg in range(shard):
         index = build_index(mine[seg * per:(seg + 1) * per], device)
-        s, i = search_index(q_repr, index, batch, topk, index_offset=rows)     # rank-local row ids for now
+        s, i = search_index(q_repr, index, batch, topk, index_offset=rows,    # rank-local row ids for now
+                            reference_ranking=reference_ranking)
         rows += index.shape[0]
         del index
         all_s.append(s)
@@ -214,7 +219,8 @@ def main(args, logger=None):
     if "LOCAL_RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1 and not dist.is_initialized():
         torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
         dist.init_process_group("nccl")
-    scores, indexes = search_distributed(q_repr, input_paths, args.shard, args.batch, args.topk, args.device)
+    scores, indexes = search_distributed(q_repr, input_paths, args.shard, args.batch, args.topk, args.device,
+                                         getattr(args, "reference_ranking", False))
     if _world() > 1 and dist.get_rank() != 0:
         return                                      # every rank holds the result; rank 0 writes the run file
     if not args.fp32_scores:

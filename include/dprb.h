@@ -58,6 +58,13 @@ enum {
   DPRB_EPI_F32_STORE = 5,      /* D(fp32) = acc + bias                                                 */
   DPRB_EPI_COUNT = 6
 };
+/* OR-ed into `epilogue`: the named 16-bit operand holds IEEE fp16 instead of bf16 (tcgen05 kind::f16 takes either
+ * format per operand).  The encoder keeps its residual stream - LayerNorm inputs and outputs - in fp16 (11 significand
+ * bits in the same 2 bytes): these are the tensors HF's autocast keeps in fp32 (modeling_bert.py:296-298, :354-356
+ * run LayerNorm and the residual add outside the 16-bit region).  AUX / OUT apply to the BIAS and BIAS_RESIDUAL
+ * epilogues. */
+enum { DPRB_GEMM_A_F16 = 0x100, DPRB_GEMM_B_F16 = 0x200, DPRB_GEMM_AUX_F16 = 0x400, DPRB_GEMM_OUT_F16 = 0x800 };
+/* (A_F16 and B_F16 must be given together: the hardware rejects an fp16 x bf16 operand pair.) */
 int dprb_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int64_t lda, int64_t ldb,
                    int64_t ldd, int a_mn_major, int b_mn_major, int epilogue, const float* bias,
                    const void* aux, int64_t ld_aux, void* out2, float alpha, int splits, float* colsum,
@@ -76,7 +83,12 @@ int dprb_gemm_profile_read(double* total_ms, double* total_flops, int64_t* launc
 int dprb_embed_ln_fwd(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, const float* word,
                       const float* pos, const float* type, const float* gamma, const float* beta, void* y_bf16,
                       float* stats, int T, int H, int vocab, int max_pos, int type_vocab, float eps,
-                      float dropout_p, uint64_t dropout_seed, dprb_stream_t stream);
+                      float dropout_p, uint64_t dropout_seed, void* y_res_f16, dprb_stream_t stream);
+/* The residual stream in fp16.  y_res_f16 (here and in dprb_ln_fwd, optional): a second copy of the LayerNorm output
+ * in IEEE fp16, read by the NEXT residual add (DPRB_GEMM_AUX_F16) while the bf16 copy y feeds the next GEMM - kind::f16
+ * cannot mix fp16 activations with bf16 weights, and HF's autocast keeps exactly this path (LayerNorm output ->
+ * residual add -> LayerNorm input) out of 16-bit bf16.  z_f16 (dprb_ln_fwd / dprb_ln_bwd): the pre-LayerNorm sum z,
+ * written by a DPRB_GEMM_OUT_F16 epilogue, holds fp16. */
 /* Backward: dz = LN'(dy); dgamma/dbeta accumulated; scatter-add of dz into the three table grads. */
 int dprb_embed_ln_bwd(const void* dy_bf16, const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids,
                       const float* word, const float* pos, const float* type, const float* gamma,
@@ -90,7 +102,8 @@ int dprb_embed_ln_bwd(const void* dy_bf16, const int64_t* ids, const int64_t* ty
  * cls_out[t / cls_stride, :] — the CLS pooling + .clone() of hf_model.py:39-41.
  * ------------------------------------------------------------------------------------------- */
 int dprb_ln_fwd(const void* z_bf16, const float* gamma, const float* beta, void* y_bf16, float* stats,
-                float* cls_out, int cls_stride, int T, int H, float eps, dprb_stream_t stream);
+                float* cls_out, int cls_stride, int T, int H, float eps, int z_f16, void* y_res_f16,
+                dprb_stream_t stream);
 /* dz = LN'(dy; z, stats); dgamma += sum dy*xhat; dbeta += sum dy; if dbias != NULL: dbias += sum_t dz
  * (the bias gradient of the Linear that produced z).  If dy_cls != NULL, dy is implicit: zero
  * everywhere except rows t % cls_stride == 0 which take dy_cls[t / cls_stride, :] (fp32). */
@@ -99,7 +112,7 @@ int dprb_ln_fwd(const void* z_bf16, const float* gamma, const float* beta, void*
 int dprb_ln_bwd(const void* dy_bf16, const float* dy_cls, int cls_stride, const void* z_bf16,
                 const float* stats, const float* gamma, void* dz_bf16, float* dgamma, float* dbeta,
                 float* dbias, int T, int H, void* dzm_bf16, float dropout_p, uint64_t dropout_site_seed,
-                dprb_stream_t stream);
+                int z_f16, dprb_stream_t stream);
 /* Dropout sites: 0 embeddings [T,H], 1 attention probabilities [nseq*heads*S, S], 2 attention-output dense [T,H],
  * 3 FFN-output dense [T,H].  Element (r, c) of a site is kept iff a 16-bit lane of hash32(r, c/2, site seed) is
  * >= round(p * 65536); site seed = fold32(dropout_seed + (layer*8 + site + 1) * 0x9E3779B97F4A7C15).
@@ -237,10 +250,14 @@ int dprb_encoder_bwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b,
  *   out_scores [Q, k] fp32 (fp32-accumulated inner products, descending; ties towards the lower row id),
  *   out_index  [Q, k] int64 = corpus row id + index_offset (the shard offset of :225-227).
  *   workspace: >= dprb_search_workspace_bytes(Q, k) bytes of device memory, caller-owned.
+ *   dtype | DPRB_SEARCH_RANK_FP16: rank by (and return) the score ROUNDED TO fp16 - what the reference's topk sees,
+ *   because its einsum on fp16 tensors returns fp16 (:150-151).  Ids then equal the reference's wherever its fp16
+ *   scores are distinct; the default ranks by the exact fp32-accumulated score (a finer, deterministic order).
  * dprb_topk_merge replaces the per-shard merge of :272-277 (topk over the concatenated shard results + gather):
  *   scores / index [Q, total] -> the k best per row (ties towards the earlier position), workspace
  *   >= dprb_topk_merge_workspace_bytes(Q, total).
  * ------------------------------------------------------------------------------------------- */
+enum { DPRB_SEARCH_RANK_FP16 = 0x100 };
 int64_t dprb_search_workspace_bytes(int64_t Q, int k);
 int dprb_search_topk(const void* queries, const void* corpus, int dtype, int64_t Q, int64_t N, int d, int k,
                      int64_t index_offset, float* out_scores, int64_t* out_index, void* workspace,

@@ -86,19 +86,51 @@ def check_gemm(M, N, K, a_mn=False, b_mn=False, epilogue=ops.EPI_BIAS, splits=1,
     return res
 
 
-# ------------------------------------------------------------------ LayerNorm / embeddings
-def check_ln(T=777, H=768, cls_stride=0, seed=1):
+def check_gemm_f16_stream(M=384, N=768, K=512, seed=30):
+    """The encoder's fp16 residual stream through the GEMM epilogue: bf16 operands, residual aux read as fp16, sum written
+    as fp16 (DPRB_GEMM_{AUX,OUT}_F16); and the both-operands-fp16 form of the MMA (a mixed fp16 x bf16 pair is rejected)."""
     g = torch.Generator().manual_seed(seed)
-    z = _bf(torch.randn(T, H, generator=g) * 2 + 0.3)
+    A = _bf(torch.randn(M, K, generator=g))
+    B = _bf(torch.randn(N, K, generator=g) * 0.5)
+    bias = torch.randn(N, generator=g)
+    aux = (torch.randn(M, N, generator=g) * 3).half()
+    res = {}
+    out = torch.empty(M, N, dtype=torch.float16, device=DEV)
+    ops.gemm(A.to(DEV), B.to(DEV), out, M, N, K, K, K, N, False, False,
+             ops.EPI_BIAS_RESIDUAL | ops.GEMM_AUX_F16 | ops.GEMM_OUT_F16, bias.to(DEV), aux.to(DEV), N)
+    want = A.double() @ B.double().T + bias.double() + aux.double()
+    _close("gemm_f16_stream", out, want, 2 ** -10, 1e-3, res)          # fp16 output: 11 significand bits
+    Ah, Bh = A.half(), B.half()
+    out2 = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(Ah.to(DEV), Bh.to(DEV), out2, M, N, K, K, K, N, False, False, ops.EPI_BIAS | ops.GEMM_A_F16 | ops.GEMM_B_F16,
+             bias.to(DEV))
+    _close("gemm_f16_ab", out2, Ah.double() @ Bh.double().T + bias.double(), 2 ** -7, 1e-3, res)
+    try:
+        ops.gemm(Ah.to(DEV), B.to(DEV), out2, M, N, K, K, K, N, False, False, ops.EPI_BIAS | ops.GEMM_A_F16, bias.to(DEV))
+        raise AssertionError("mixed fp16 x bf16 operands must be rejected on the host")
+    except Exception as e:  # noqa
+        assert "fp16 x bf16" in str(e), e
+    return res
+
+
+# ------------------------------------------------------------------ LayerNorm / embeddings
+def check_ln(T=777, H=768, cls_stride=0, seed=1, f16=False):
+    """f16: z arrives in fp16 (written by a DPRB_GEMM_OUT_F16 epilogue) and the fp16 residual copy y_res is requested."""
+    g = torch.Generator().manual_seed(seed)
+    z = torch.randn(T, H, generator=g) * 2 + 0.3
+    z = z.half() if f16 else _bf(z)          # f16: the encoder's residual-stream format (z in / y out in fp16)
     gamma = 1 + 0.1 * torch.randn(H, generator=g)
     beta = 0.1 * torch.randn(H, generator=g)
     eps = 1e-12
     res = {}
-    y, stats, cls = ops.ln_fwd(z.to(DEV), gamma.to(DEV), beta.to(DEV), eps, cls_stride)
+    y_res = torch.empty(T, H, dtype=torch.float16, device=DEV) if f16 else None
+    y, stats, cls = ops.ln_fwd(z.to(DEV), gamma.to(DEV), beta.to(DEV), eps, cls_stride, y_res)
     zr = z.float().requires_grad_(True)
     gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
     yr = oenc.layer_norm(zr, gr, br, eps)
     _close("ln_y", y, yr, 2 ** -7, 1e-3, res)
+    if f16:
+        _close("ln_y_res", y_res, yr, 2 ** -10, 1e-3, res)
     if cls_stride:
         _close("ln_cls", cls, yr[::cls_stride], 1e-5, 1e-5, res)
     # backward
@@ -298,6 +330,10 @@ CHECKS = {
     "ln_768": lambda: check_ln(777, 768),
     "ln_1024_cls": lambda: check_ln(512, 1024, cls_stride=64),
     "ln_128": lambda: check_ln(100, 128),
+    "ln_768_f16": lambda: check_ln(777, 768, f16=True),
+    "ln_1024_cls_f16": lambda: check_ln(512, 1024, cls_stride=64, f16=True),
+    "gemm_f16_stream": lambda: check_gemm_f16_stream(),
+    "gemm_f16_stream_big": lambda: check_gemm_f16_stream(1024, 768, 3072, seed=31),
     "embed": lambda: check_embed(),
     "colsum": lambda: check_colsum(),
     "attn_128_masked": lambda: check_attention(3, 128, 2, True),

@@ -144,3 +144,37 @@ def test_rank_sharded_search_equals_single_gpu(tmp_path):
     ret = mgr.dict()
     mp.spawn(_dist_worker, args=(2, 29677, str(tmp_path), ret), nprocs=2, join=True)
     assert ret[0] == (True, True) and ret[1] == (True, True)
+
+
+def test_reference_ranking_reproduces_the_reference_run_files(tmp_path):
+    """`--reference_ranking` (rank by the fp16-rounded score): dpr_scale_b200.run_retrieval.main on the golden inputs
+    writes the SAME run files, byte for byte, that the unmodified reference main() wrote
+    (tests/golden/make_golden_retrieval.py; its inputs have pairwise distinct fp16 scores inside every top-(k+1))."""
+    import os
+    from dpr_scale_b200 import run_retrieval as RR
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "retrieval_small.npz"))
+    emb = tmp_path / "emb"
+    emb.mkdir()
+    for j in range(3):
+        with open(emb / f"reps_{j:04}.pkl", "wb") as f:
+            pickle.dump(torch.from_numpy(g[f"shard{j}"]), f, protocol=4)
+    with open(emb / "query_reps.pkl", "wb") as f:
+        pickle.dump(torch.from_numpy(g["queries"]), f, protocol=4)
+    for name in ("passages_tsv", "questions_csv", "questions_tsv"):
+        with open(tmp_path / name, "w") as f:
+            f.write(str(g[name]))
+    k = int(g["topk"])
+    for fmt, qfile, extra in (("json", "questions_csv", []), ("trec", "questions_tsv", ["--trec_format", "--run_name", "golden"])):
+        out = tmp_path / f"run.{fmt}"
+        args = RR.get_parser().parse_args(
+            ["--ctx_embeddings_dir", str(emb), "--questions_tsv_path", str(tmp_path / qfile),
+             "--passages_tsv_path", str(tmp_path / "passages_tsv"), "--output_runfile_path", str(out),
+             "--topk", str(k), "--shard", "3", "--reference_ranking"] + extra)
+        RR.main(args)
+        assert open(out).read() == str(g[f"run_{fmt}"]), fmt
+    # per segment, against the reference's own search_index outputs
+    for j in range(3):
+        idx = torch.from_numpy(g[f"shard{j}"]).to("cuda", torch.float16)
+        s, i = RR.search_index(torch.from_numpy(g["queries"]), idx, 8, k, reference_ranking=True)
+        assert np.array_equal(s.cpu().numpy().astype(np.float64), g[f"scores{j}"])
+        assert np.array_equal(i.cpu().numpy(), g[f"index{j}"].astype(np.int64))

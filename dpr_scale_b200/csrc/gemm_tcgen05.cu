@@ -545,6 +545,11 @@ EncodeTiledFn get_encode_fn() {
 // Row-major bf16 matrix [rows, cols] with leading dimension ld (elements); box = [box_rows, 64 cols], 128B swizzle.
 int make_tmap(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld, int box_rows,
               bool is_output = false, int box_cols = 64) {
+  static thread_local bool ctx_bound = false;   // driver entry point: needs a current context on THIS thread
+  if (!ctx_bound) {
+    DPRB_CHECK_CUDA(cudaFree(nullptr));
+    ctx_bound = true;
+  }
   EncodeTiledFn fn = get_encode_fn();
   DPRB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   DPRB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "gemm operand base %p not 16-byte aligned", base);

@@ -16,6 +16,8 @@
 // Backward recomputes tiles instead of reading stored logits: one launch rebuilds W = softmax - onehot for the local
 // row block [nq x C] and the local column block [Q x nc] (bf16 hi + lo), and dq = W_rows c, dc = W_cols^T q run as
 // split-K launches of the encoder's tcgen05 GEMM (fp32 atomic accumulate) on the h / m parts.
+#include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
 #include "dprb_internal.h"
 
@@ -56,7 +58,13 @@ struct ScoreParams {
   const float* lse_in;
   Region reg[2];
   int n_regions;
+  unsigned long long* dbg;   // DPRB_SCORE_DBG=1: per-CTA role timestamps [gridDim.x][8] (diagnostics only)
 };
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ float lg2_approx(float x) {
@@ -115,12 +123,19 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   const int tiles0 = p.reg[0].n_rb * p.reg[0].n_cb;
   const int tiles = tiles0 + (p.n_regions > 1 ? p.reg[1].n_rb * p.reg[1].n_cb : 0);
+  // Every CTA owns a CONTIGUOUS range of tiles in row-block-major order: consecutive tiles share the query tile (L2 /
+  // TMA reuse) and, in the forward, their row statistics merge in registers - a row block ends up with one partial per
+  // CTA that touched it (~n_cb / tiles_per_cta) instead of one per tile.
+  const int t_base = tiles / (int)gridDim.x, t_rem = tiles % (int)gridDim.x;
+  const int t_begin = (int)blockIdx.x * t_base + min((int)blockIdx.x, t_rem);
+  const int t_end = t_begin + t_base + ((int)blockIdx.x < t_rem ? 1 : 0);
 
   if (warp == 0) {
     if (lane == 0) {
+      if (p.dbg) p.dbg[blockIdx.x * 8 + 0] = gtime();
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+      for (int t = t_begin; t < t_end; ++t) {
         const Region& g = p.reg[t < tiles0 ? 0 : 1];
         const int tt = t < tiles0 ? t : t - tiles0;
         const int row0 = g.r0 + (tt / g.n_cb) * TM, col0 = g.c0 + (tt % g.n_cb) * TN;
@@ -136,6 +151,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if (p.dbg) p.dbg[blockIdx.x * 8 + 1] = gtime();
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -143,7 +159,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       constexpr uint32_t idesc = make_idesc_bf16_f32(TM, TN, 0, 0);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+      for (int t = t_begin; t < t_end; ++t) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem + acc * TN;
@@ -167,6 +183,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         umma_commit(&tfull[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if (p.dbg) p.dbg[blockIdx.x * 8 + 2] = gtime();
     }
     __syncwarp();
   } else if (warp >= 4) {
@@ -176,10 +193,67 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const float sc2 = p.inv_t * LOG2E;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+    // forward: statistics of the row block in progress (thread = row), flushed when the row block changes
+    float m2 = -INFINITY, l = 0.f, pick = 0.f;
+    int cur_rb = -1;
+    auto cta_of = [&](int t) {       // inverse of the contiguous tile ranges above
+      const int big = t_rem * (t_base + 1);
+      return t < big ? t / (t_base + 1) : t_rem + (t - big) / max(t_base, 1);
+    };
+    auto flush = [&](int rb) {
+      // one partial per (row block, CTA); the LAST CTA to deliver one folds them into lse + loss
+      const Region& g = p.reg[0];
+      const int row = rb * TM + tid;
+      const bool row_ok = row < p.Q;
+      const int lo = cta_of(rb * g.n_cb), hi = cta_of(rb * g.n_cb + g.n_cb - 1);
+      const int nslots = hi - lo + 1, slot = (int)blockIdx.x - lo;
+      const long long plane = (long long)g.n_cb * p.Qpad;
+      if (row_ok) {
+        float* pm = p.part + (long long)slot * p.Qpad + row;
+        __stcg(pm, m2);
+        __stcg(pm + plane, l);
+        __stcg(pm + 2 * plane, pick);
+      }
+      __threadfence();
+      named_bar_sync(2, EPI_THREADS);
+      if (tid == 0) *sFlag = (atomicAdd(p.counters + rb, 1) == nslots - 1) ? 1 : 0;
+      named_bar_sync(2, EPI_THREADS);
+      if (*sFlag) {
+        __threadfence();
+        float loss = 0.f;
+        if (row_ok) {
+          const float* base = p.part + row;
+          float M = -INFINITY;
+#pragma unroll 4
+          for (int b = 0; b < nslots; ++b) M = fmaxf(M, __ldcg(base + (long long)b * p.Qpad));
+          float L = 0.f, P = 0.f;
+          const float Mf = (M == -INFINITY) ? 0.f : M;       // all-masked row: every l is 0
+#pragma unroll 4
+          for (int b = 0; b < nslots; ++b) {
+            const float mb = __ldcg(base + (long long)b * p.Qpad);
+            const float lb = __ldcg(base + plane + (long long)b * p.Qpad);
+            P += __ldcg(base + 2 * plane + (long long)b * p.Qpad);   // one slot saw the label, the others hold 0
+            L = fmaf(lb, ex2_approx(mb - Mf), L);              // mb = -inf: lb = 0 and ex2(-inf) = 0
+          }
+          const float lse = (M == -INFINITY) ? -INFINITY : (M + lg2_approx(L)) * LN2;
+          p.lse[row] = lse;
+          loss = lse - P;
+        }
+        loss = warp_sum(loss);
+        if (lane == 0 && p.loss_sum != nullptr) atomicAdd(p.loss_sum, loss);
+        if (tid == 0) p.counters[rb] = 0;                      // ready for the next call
+      }
+      named_bar_sync(2, EPI_THREADS);                          // sFlag is rewritten by the next flush
+    };
+    for (int t = t_begin; t < t_end; ++t) {
       const Region& g = p.reg[t < tiles0 ? 0 : 1];
       const int tt = t < tiles0 ? t : t - tiles0;
       const int rb = tt / g.n_cb, cb = tt % g.n_cb;
+      if (MODE == 0 && rb != cur_rb) {
+        if (cur_rb >= 0) flush(cur_rb);
+        m2 = -INFINITY; l = 0.f; pick = 0.f;
+        cur_rb = rb;
+      }
       const int row = g.r0 + rb * TM + tid;                  // global query row of this thread
       const int colbase = g.c0 + cb * TN;
       const int col_end = g.c0 + g.nc;                       // exclusive (== C in forward)
@@ -196,7 +270,6 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tcgen05_fence_after();
       const uint32_t tbase = tmem + lane_addr + acc * TN;
       if (MODE == 0) {
-        float m2 = -INFINITY, l = 0.f, pick = 0.f;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t r[32];
@@ -234,13 +307,6 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             for (int j = 0; j < 32; ++j) l += ex2_approx(s2[j] - m2);
           }
           __syncwarp();
-        }
-        if (row_ok) {
-          float* pm = p.part + (long long)cb * p.Qpad + row;
-          const long long plane = (long long)g.n_cb * p.Qpad;
-          __stcg(pm, m2);
-          __stcg(pm + plane, l);
-          __stcg(pm + 2 * plane, pick);
         }
       } else {
         const float lse2 = row_ok ? p.lse_in[row] * LOG2E : INFINITY;
@@ -296,37 +362,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-
-      if (MODE == 0) {
-        // the LAST tile of a row block (whichever CTA finishes it) folds the per-column-block partials
-        __threadfence();
-        named_bar_sync(2, EPI_THREADS);
-        if (tid == 0) *sFlag = (atomicAdd(p.counters + rb, 1) == g.n_cb - 1) ? 1 : 0;
-        named_bar_sync(2, EPI_THREADS);
-        if (*sFlag) {
-          __threadfence();
-          float loss = 0.f;
-          if (row_ok) {
-            const long long plane = (long long)g.n_cb * p.Qpad;
-            float M = -INFINITY;
-            for (int b = 0; b < g.n_cb; ++b) M = fmaxf(M, __ldcg(p.part + (long long)b * p.Qpad + row));
-            float L = 0.f, P = 0.f;
-            for (int b = 0; b < g.n_cb; ++b) {
-              const float mb = __ldcg(p.part + (long long)b * p.Qpad + row);
-              if (mb != -INFINITY) L += __ldcg(p.part + plane + (long long)b * p.Qpad + row) * ex2_approx(mb - M);
-              P += __ldcg(p.part + 2 * plane + (long long)b * p.Qpad + row);   // one block saw the label, others hold 0
-            }
-            const float lse = (M == -INFINITY) ? -INFINITY : (M + lg2_approx(L)) * LN2;
-            p.lse[row] = lse;
-            loss = lse - P;
-          }
-          loss = warp_sum(loss);
-          if (lane == 0 && p.loss_sum != nullptr) atomicAdd(p.loss_sum, loss);
-          if (tid == 0) p.counters[rb] = 0;                  // ready for the next call
-        }
-        named_bar_sync(2, EPI_THREADS);                      // sFlag is rewritten by the next tile
-      }
     }
+    if (MODE == 0 && cur_rb >= 0) flush(cur_rb);
+    if (p.dbg && tid == 0) p.dbg[blockIdx.x * 8 + 3] = gtime();
   }
 
   tcgen05_fence_before();
@@ -334,6 +372,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc(tmem, 256);
+    if (p.dbg && lane == 0) p.dbg[blockIdx.x * 8 + 4] = gtime();
   }
 }
 
@@ -355,6 +394,13 @@ EncodeTiledFn encode_fn() {
 
 // bf16 [2 parts][rows][d]; box = [1][128 rows][64 cols], 128B swizzle; rows / columns beyond the extent are zero-filled
 int make_tmap_parts(CUtensorMap* out, const void* base, long long rows, long long d) {
+  // cuTensorMapEncodeTiled is a DRIVER call: it needs a current context on the calling thread.  Backward runs on
+  // autograd's worker thread, where this may be the first CUDA call of any kind - bind the primary context first.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    DPRB_CHECK_CUDA(cudaFree(nullptr));
+    ctx_bound = true;
+  }
   EncodeTiledFn fn = encode_fn();
   DPRB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)rows, 2};
@@ -453,8 +499,27 @@ int score_tc_fwd(const float* q, const float* c, const uint8_t* col_mask, const 
   int sms = num_sms();
   if (sms <= 0) sms = 148;
   const int tiles = w.n_rb * w.n_cb;
-  score_tc_kernel<0><<<tiles < sms ? tiles : sms, THREADS, SMEM_BYTES, stream>>>(tq, tc, p);
+  static unsigned long long* dbg = nullptr;
+  static const bool want_dbg = getenv("DPRB_SCORE_DBG") != nullptr;
+  if (want_dbg && dbg == nullptr) DPRB_CHECK_CUDA(cudaMalloc(&dbg, 148 * 8 * 8));
+  p.dbg = want_dbg ? dbg : nullptr;
+  const int grid = tiles < sms ? tiles : sms;
+  score_tc_kernel<0><<<grid, THREADS, SMEM_BYTES, stream>>>(tq, tc, p);
   DPRB_LAUNCH_CHECK();
+  if (want_dbg) {
+    static int calls = 0;
+    if (++calls == 3) {   // a warmed-up launch
+      unsigned long long h[148 * 8];
+      DPRB_CHECK_CUDA(cudaStreamSynchronize(stream));
+      DPRB_CHECK_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
+      unsigned long long t0 = ~0ull;
+      for (int i = 0; i < grid; ++i) if (h[i * 8] < t0) t0 = h[i * 8];
+      for (int i = 0; i < grid; ++i)
+        fprintf(stderr, "[score dbg] cta %3d start %7.1f producer_end %7.1f mma_end %7.1f epi_end %7.1f dealloc %7.1f us\n", i,
+                (h[i * 8] - t0) / 1e3, (h[i * 8 + 1] - t0) / 1e3, (h[i * 8 + 2] - t0) / 1e3, (h[i * 8 + 3] - t0) / 1e3,
+                (h[i * 8 + 4] - t0) / 1e3);
+    }
+  }
   return 0;
 }
 

@@ -176,5 +176,12 @@ def test_reference_ranking_reproduces_the_reference_run_files(tmp_path):
     for j in range(3):
         idx = torch.from_numpy(g[f"shard{j}"]).to("cuda", torch.float16)
         s, i = RR.search_index(torch.from_numpy(g["queries"]), idx, 8, k, reference_ranking=True)
-        assert np.array_equal(s.cpu().numpy().astype(np.float64), g[f"scores{j}"])
-        assert np.array_equal(i.cpu().numpy(), g[f"index{j}"].astype(np.int64))
+        sc, ids, gold = s.cpu().numpy().astype(np.float64), i.cpu().numpy(), g[f"index{j}"].astype(np.int64)
+        assert np.array_equal(sc, g[f"scores{j}"])
+        # inside ONE segment fp16 scores may tie (the generator only separates the merged top-(k+1)); torch.topk's order
+        # among equal scores is unspecified, so ids are compared where the score is unique in its row
+        uniq = np.ones_like(sc, dtype=bool)
+        uniq[:, 1:] &= sc[:, 1:] != sc[:, :-1]
+        uniq[:, :-1] &= sc[:, :-1] != sc[:, 1:]
+        uniq[:, -1] = False
+        assert uniq.mean() > 0.8 and np.array_equal(ids[uniq], gold[uniq])

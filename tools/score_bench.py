@@ -23,7 +23,9 @@ def timeit(f, iters=20):
     return e0.elapsed_time(e1) / iters * 1e3
 
 
-for Q, C, nq, nc in ((128, 1024, 128, 1024), (1024, 8192, 128, 1024)):
+_a = [int(x) for x in sys.argv[1:]]
+SHAPES = [tuple(_a[i:i + 4]) for i in range(0, len(_a), 4)] or [(128, 1024, 128, 1024), (1024, 8192, 128, 1024)]
+for Q, C, nq, nc in SHAPES:
     d = 768
     q, c = torch.randn(Q, d, device="cuda"), torch.randn(C, d, device="cuda")
     mask = torch.zeros(C, dtype=torch.uint8, device="cuda")

@@ -67,6 +67,7 @@ struct GemmParams {
   int aux_prefetch;    // 1: request aux with cp.async before waiting for the accumulator (CG = 2 only)
   Drop drop;           // EPI_BIAS_RESIDUAL only: D = dropout(acc + bias) + aux  (hidden dropout before the residual)
   uint32_t idesc;      // UMMA instruction descriptor (operand formats: bf16 or fp16 per operand)
+  int dynamic;         // 1: work units are handed out by cluster launch control (see below); 0: static striding
   int aux_f16, out_f16;  // aux / D hold fp16 instead of bf16 (the encoder's fp16 residual stream)
 };
 
@@ -120,6 +121,54 @@ __device__ __forceinline__ void tma_store_wait_read_n(int slabs_in_flight) {
   else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 }
 
+// ---- dynamic persistent scheduling with cluster launch control (sm_100 CLC) ----------------------------------
+// The grid has ONE cluster per work unit.  The clusters that get SMs process their own unit and then keep stealing
+// units from clusters that have not been launched yet (clusterlaunchcontrol.try_cancel): a cancelled cluster never
+// runs, its unit index (its first ctaid.x / 2) is executed by the thief.  Unlike a static `u += num_workers` loop this
+// stays efficient when some SMs are busy with other kernels - NCCL's all-reduce CTAs during backward, the query
+// encoder's kernels on the side stream - because nobody waits for a CTA that could not become resident: the measured
+// cost of that wait was +2.8 ms of GEMM time per step at N = 2 (gemm_ms 61.0 -> 64.4).
+// Protocol (2 response slots, so the next unit is requested while the current one is computed): warp 3 of EVERY CTA
+// arms its CTA's clc_full[slot] (expect_tx 16) once its local consumers have released the slot and signals the
+// leader; the leader's warp 3 then issues ONE multicast try_cancel whose 16-byte response lands in both CTAs.  The
+// consumers (TMA thread, MMA thread, lane 0 of each epilogue warp) wait on clc_full, decode, release clc_empty.
+__device__ __forceinline__ void clc_try_cancel_multicast(void* resp, uint64_t* bar) {
+  asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];"
+               ::"r"(smem_u32(resp)), "r"(smem_u32(bar)) : "memory");
+}
+// returns the stolen cluster's first ctaid.x, or -1 when nothing was left to cancel
+__device__ __forceinline__ int clc_decode(const void* resp) {
+  uint64_t lo, hi;
+  asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(smem_u32(resp)) : "memory");
+  uint32_t ok, x;
+  asm volatile(
+      "{\n\t.reg .b128 r;\n\t.reg .pred p;\n\t"
+      "mov.b128 r, {%2, %3};\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p, r;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "@p clusterlaunchcontrol.query_cancel.get_first_ctaid::x.b32.b128 %1, r;\n\t"
+      "@!p mov.u32 %1, 0;\n\t}"
+      : "=r"(ok), "=r"(x) : "l"(lo), "l"(hi));
+  return ok ? (int)x : -1;
+}
+struct UnitCursor {       // one per consumer thread
+  int slot;
+  uint32_t phase;
+};
+// next work unit of this cluster (or -1): static striding, or the response of the pending CLC request
+__device__ __forceinline__ int next_unit(int dynamic, int u, int num_workers, int units, UnitCursor& c, uint64_t* clc_full,
+                                         uint64_t* clc_empty, const uint8_t* clc_resp) {
+  if (!dynamic) {
+    u += num_workers;
+    return u < units ? u : -1;
+  }
+  mbar_wait(&clc_full[c.slot], c.phase);
+  const int x = clc_decode(clc_resp + c.slot * 16);
+  mbar_arrive(&clc_empty[c.slot]);
+  if (++c.slot == 2) { c.slot = 0; c.phase ^= 1; }
+  return x < 0 ? -1 : (x >> 1);
+}
+
 template <int A_MN, int B_MN, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -139,6 +188,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* tmem_full_bar = bars + 2 * STAGES;     // [ACC_STAGES]
   uint64_t* tmem_empty_bar = tmem_full_bar + ACC_STAGES;  // (CG=2: only the leader's are used)
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + ACC_STAGES);
+  uint64_t* clc_full = tmem_empty_bar + ACC_STAGES + 1;   // [2]
+  uint64_t* clc_empty = clc_full + 2;                      // [2]
+  uint64_t* clc_ready = clc_empty + 2;                     // [2] (leader's are used)
+  uint8_t* clc_resp = reinterpret_cast<uint8_t*>(bars) + 208;   // [2][16], 16-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -162,6 +215,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], NUM_EPI_WARPS * CG);  // epilogue warps of both CTAs release the leader's MMA
     }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&clc_full[i], 1);                                         // the local arming arrive (+ 16 response bytes)
+      mbar_init(&clc_empty[i], NUM_EPI_WARPS + 1 + (is_leader ? 1 : 0));  // local consumers: TMA, (MMA), epilogue warps
+      mbar_init(&clc_ready[i], CG);                                       // both CTAs have armed their clc_full
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -181,7 +239,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = worker; u < units; u += num_workers) {
+      UnitCursor cur = {0, 0};
+      for (int u = worker; u >= 0; u = next_unit(p.dynamic, u, num_workers, units, cur, clc_full, clc_empty, clc_resp)) {
         const int tile = u % tiles, split = u / tiles;
         const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
         const int m0 = m_blk * m_rows_per_unit + (int)cta_rank * CTA_M;        // this CTA's A rows
@@ -230,7 +289,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int u = worker; u < units; u += num_workers) {
+      UnitCursor cur = {0, 0};
+      for (int u = worker; u >= 0; u = next_unit(p.dynamic, u, num_workers, units, cur, clc_full, clc_empty, clc_resp)) {
         const int split = u / tiles;
         const int kb0 = split * p.k_blocks_per_split;
         const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
@@ -258,6 +318,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
     __syncwarp();
+  } else if (warp == 3) {
+    // ================================ CLC scheduler (one thread per CTA) ================================
+    if (lane == 0 && p.dynamic) {
+      int slot = 0;
+      uint32_t ph = 0;
+      for (;;) {
+        mbar_wait(&clc_empty[slot], ph ^ 1);                 // local consumers are done with this slot's old response
+        mbar_arrive_expect_tx(&clc_full[slot], 16);          // arm: the response is 16 bytes
+        if (CG == 2 && !is_leader) mbar_arrive_remote(&clc_ready[slot], 0);
+        else mbar_arrive(&clc_ready[slot]);
+        if (is_leader) {
+          mbar_wait(&clc_ready[slot], ph);                   // both CTAs armed
+          clc_try_cancel_multicast(clc_resp + slot * 16, &clc_full[slot]);
+        }
+        mbar_wait(&clc_full[slot], ph);
+        const int x = clc_decode(clc_resp + slot * 16);
+        if (x < 0) break;                                    // nothing left to steal: no further requests
+        if (++slot == 2) { slot = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
   } else if (warp >= 4) {
     // ================================ epilogue warps ================================
     // Warp (quarter, col_half) owns TMEM lanes [32*quarter, +32) x columns [128*col_half, +128) of this CTA's
@@ -275,7 +356,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const bool is_gelu = (p.epilogue == DPRB_EPI_BIAS_GELU);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = worker; u < units; u += num_workers) {
+    UnitCursor cur = {0, 0};
+    for (int u = worker; u >= 0;) {
       const int tile = u % tiles;
       const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
       const int row0 = m_blk * m_rows_per_unit + (int)cta_rank * CTA_M + quarter * 32;
@@ -299,7 +381,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         }
         cp_async_commit();
-        const int un = u + num_workers;
+        const int un = p.dynamic ? units : u + num_workers;   // (dynamic: the next unit is not known yet)
         if (un < units) {
           const int tn = un % tiles;
           const int rn = (tn / p.num_n_blocks) * m_rows_per_unit + (int)cta_rank * CTA_M + quarter * 32 + lane;
@@ -511,6 +593,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         else mbar_arrive(&tmem_empty_bar[acc]);
       }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      int nu = 0;
+      if (lane == 0) nu = next_unit(p.dynamic, u, num_workers, units, cur, clc_full, clc_empty, clc_resp);
+      u = __shfl_sync(0xFFFFFFFFu, nu, 0);
     }
     if (lane == 0) tma_store_wait_all();  // smem must stay valid until the last bulk store has drained
     __syncwarp();
@@ -666,7 +751,9 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long l
                "gemm: colsum is supported for the BIAS / BIAS_RESIDUAL / DGELU epilogues only");
 
   const int units = tiles * p.splits;
-  const int grid = (units < workers ? units : workers) * CG;
+  static const bool static_sched = (std::getenv("DPRB_GEMM_STATIC") != nullptr);
+  p.dynamic = (CG == 2 && !static_sched && units > workers) ? 1 : 0;
+  const int grid = p.dynamic ? units * CG : (units < workers ? units : workers) * CG;
 
   static bool attr_set = false;
   if (!attr_set) {

@@ -86,19 +86,27 @@ def test_generation_tasks_host_logic(tmp_path):
     from dpr_scale_b200.task.dpr_eval_task import GenerateEmbeddingsTask, GenerateQueryEmbeddingsTask
     kw = dict(transform={}, model={}, datamodule=None, optim={})
     t = GenerateEmbeddingsTask(ctx_embeddings_dir=str(tmp_path / "emb"), checkpoint_path="", **kw)
-    parts = [torch.arange(6, dtype=torch.float32).view(2, 3) + 10 * i for i in range(3)]
-    path = t.test_epoch_end([t._to_pinned(p) for p in parts])
+    t._encode = lambda tokens: tokens                 # stand-in for the encoder: the "tokens" are the embeddings
+    # more batches than ring slots (pinned buffers are reused), ragged batch sizes
+    parts = [torch.arange(3 * (2 + i % 3), dtype=torch.float32).view(-1, 3) + 10 * i for i in range(2 * t.RING + 3)]
+    rows = [t.test_step({"contexts_ids": p}, i) for i, p in enumerate(parts)]
+    assert rows == [p.shape[0] for p in parts]        # nothing but row counts is kept per batch
+    path = t.test_epoch_end(rows)
     assert path.endswith("emb/reps_0000.pkl")
     raw = open(path, "rb").read()
     assert raw[:2] == b"\x80\x04"                                  # pickle protocol 4
     assert torch.equal(pickle.loads(raw), torch.cat(parts))
     q = GenerateQueryEmbeddingsTask(ctx_embeddings_dir=str(tmp_path / "emb"), checkpoint_path="", **kw)
+    q._encode = lambda tokens: tokens
     assert q.query_emb_output_path == str(tmp_path / "emb" / "query_reps.pkl")
-    out = q.test_epoch_end(parts)
-    assert torch.equal(pickle.load(open(out, "rb")), torch.cat(parts))
+    out = q.test_epoch_end([q.test_step({"query_ids": p}, i) for i, p in enumerate(parts[:3])])
+    assert torch.equal(pickle.load(open(out, "rb")), torch.cat(parts[:3]))
     q2 = GenerateQueryEmbeddingsTask(ctx_embeddings_dir=str(tmp_path / "emb"), checkpoint_path="",
                                      query_emb_output_path=str(tmp_path / "x" / "q.pkl"), **kw)
-    assert q2.test_epoch_end(parts) == str(tmp_path / "x" / "q.pkl")
+    q2._encode = lambda tokens: tokens
+    q2.test_step({"query_ids": parts[0]}, 0)
+    assert q2.test_epoch_end([2]) == str(tmp_path / "x" / "q.pkl")
+    assert torch.equal(pickle.load(open(tmp_path / "x" / "q.pkl", "rb")), parts[0])
 
 
 def test_generation_configs_compose():

@@ -437,7 +437,8 @@ def run_b200(args, workload):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        from dpr_scale_b200.utils.dist_init import init_process_group
+        init_process_group(dev)          # NCCL, high-priority stream (see utils/dist_init.py)
     check = None
     if world > 1 and not args.no_selfcheck:
         check = selfcheck(world, rank, dev)

@@ -26,9 +26,8 @@ def run(argv, target):
         name = argv[i + 1].replace(".yaml", "")
         del argv[i:i + 2]
     argv = [a for a in argv if a != "-m"]
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not dist.is_initialized():
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-        dist.init_process_group("nccl")
+    from .utils.dist_init import init_process_group
+    init_process_group()
     cfg = compose(name, argv)
     cfg.task.datamodule = None
     cfg.task._target_ = target

@@ -19,13 +19,8 @@ def init_distributed():
     """One process per GPU under torchrun: bind the device and join the NCCL group BEFORE the Trainer reads the world
     size (what Lightning's DDP strategy does inside `Trainer.fit`, main.py:32-44 of the reference).  Without it every
     rank would train alone on cuda:0."""
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1 and not dist.is_initialized():
-        backend = os.environ.get("DPRB_DIST_BACKEND", "nccl" if torch.cuda.is_available() else "gloo")
-        if torch.cuda.is_available():
-            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-        dist.init_process_group(backend)
-    return world
+    from .utils.dist_init import init_process_group
+    return init_process_group()
 
 
 def main(argv=None):

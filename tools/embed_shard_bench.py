@@ -48,7 +48,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        from dpr_scale_b200.utils.dist_init import init_process_group
+        init_process_group(dev)
     from dpr_scale_b200.task.dpr_eval_task import GenerateEmbeddingsTask
     task = GenerateEmbeddingsTask(ctx_embeddings_dir=args.out, checkpoint_path="", transform={}, datamodule=None,
                                   optim={}, shared_model=False,

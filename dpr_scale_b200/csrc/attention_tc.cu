@@ -43,11 +43,17 @@ __device__ __forceinline__ void st_chunk(uint8_t* tile, int row, int chunk, cons
 }
 
 // ------------------------------------------------------------------------------------------ forward
-// smem: sQ | sK | sV | sP (2 k-blocks) | mask[2][128] | barriers.  TMEM: S cols [0,128), O cols [128,192).
-constexpr int FWD_SMEM = 3 * TILE_BYTES + 2 * TILE_BYTES + 2 * 128 * 4 + 64 + 1024;
+// smem: sQ | sK | sV | mask[2][128] | barriers (51 KB) - the two P k-blocks ALIAS sQ | sK (both are dead once the S MMA
+// has completed, which is what the softmax threads wait for before they write P), and the staged output aliases sQ again
+// once the P V MMA has completed.  TMEM: S cols [0,128); O reuses cols [0,64) (S is dead once P has been written).
+// => 128 TMEM columns and 51 KB per CTA: FOUR co-resident CTAs per SM (was two at 83 KB / 256 columns).  Each CTA is a
+// serial load -> MMA -> softmax -> MMA -> store chain of ~6 us per (sequence, head); with two in flight the SM moved
+// 2.84 TB/s chip-wide (0.44 of the HBM peak, ncu r1), bounded by that chain's latency, not by bandwidth.
+constexpr int FWD_SMEM = 3 * TILE_BYTES + 2 * 128 * 4 + 64 + 1024;
+constexpr int FWD_CTAS_PER_SM = 4;
 
 template <bool DROP>
-__global__ void __launch_bounds__(NTHREADS, 2)
+__global__ void __launch_bounds__(NTHREADS, FWD_CTAS_PER_SM)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_ctx,
                    const int32_t* __restrict__ attn_mask, float* __restrict__ lse_out, int S, int heads, int nseq,
                    Drop drop) {
@@ -56,8 +62,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + TILE_BYTES;
   uint8_t* sV = sK + TILE_BYTES;
-  uint8_t* sP = sV + TILE_BYTES;  // 2 x 16 KB
-  float* sMask = reinterpret_cast<float*>(sP + 2 * TILE_BYTES);  // [2][128]
+  uint8_t* sP = sQ;               // 2 x 16 KB over sQ | sK (see above)
+  float* sMask = reinterpret_cast<float*>(sV + TILE_BYTES);  // [2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + 256);
   uint64_t *b_load = bars, *b_s = bars + 1, *b_p = bars + 2, *b_o = bars + 3, *b_free = bars + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
@@ -72,13 +78,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, 128);
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tO = tmem + 128;
+  const uint32_t tS = tmem, tO = tmem;
   const int nprob = nseq * heads;
 
   if (warp == 0) {
@@ -130,7 +136,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       tcgen05_fence_after();
       // pass 1: row max (TMEM reads are cheap: re-reading S beats holding 128 scores in registers)
       float m = -INFINITY;
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
         tmem_ld_32x32(tS + lane_addr + c * 32, r);
@@ -141,7 +147,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       const float e = (m == -INFINITY) ? 0.f : m;  // fully masked row guard
       // pass 2: P = exp2(s - max) -> bf16 -> swizzled smem (A operand of P V), row sum
       float l = 0.f;
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
         tmem_ld_32x32(tS + lane_addr + c * 32, r);
@@ -177,7 +183,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       const float inv = l > 0.f ? 1.f / l : 0.f;
       mbar_wait(b_o, ph);
       tcgen05_fence_after();
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
         tmem_ld_32x32(tO + lane_addr + c * 32, r);
@@ -207,7 +213,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   __syncthreads();
   if (warp == 0) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem, 256);
+    tmem_dealloc(tmem, 128);
   }
 }
 
@@ -515,7 +521,7 @@ int attn_fwd_tc(const void* qkv, const int32_t* attn_mask, void* ctx, float* lse
   int sms = num_sms();
   if (sms <= 0) sms = 148;
   const int nprob = nseq * heads;
-  const int grid = nprob < 2 * sms ? nprob : 2 * sms;  // two co-resident CTAs per SM interleave their serial chains
+  const int grid = nprob < FWD_CTAS_PER_SM * sms ? nprob : FWD_CTAS_PER_SM * sms;  // co-resident CTAs interleave their serial chains
   if (drop.on()) attn_fwd_tc_kernel<true><<<grid, NTHREADS, FWD_SMEM, stream>>>(tq, tc, attn_mask, lse, S, heads, nseq, drop);
   else attn_fwd_tc_kernel<false><<<grid, NTHREADS, FWD_SMEM, stream>>>(tq, tc, attn_mask, lse, S, heads, nseq, drop);
   DPRB_LAUNCH_CHECK();

@@ -438,18 +438,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint32_t r[32];
           tmem_ld_32x32(tbase + h * 32, r);
           tmem_ld_wait();
-          float v[32];
+          // pairs of adjacent accumulator columns go through the packed-fp32 pipe (FFMA2): bias, GELU and its derivative
+          float2 v2[16];
+          const float2 al = make_float2(p.alpha, p.alpha);
           if (p.bias != nullptr && col0 + 32 <= p.N) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-              v[j] = fmaf(__uint_as_float(r[j]), p.alpha, b.x); v[j + 1] = fmaf(__uint_as_float(r[j + 1]), p.alpha, b.y);
-              v[j + 2] = fmaf(__uint_as_float(r[j + 2]), p.alpha, b.z); v[j + 3] = fmaf(__uint_as_float(r[j + 3]), p.alpha, b.w);
+              v2[j >> 1] = __ffma2_rn(make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), al, make_float2(b.x, b.y));
+              v2[(j >> 1) + 1] = __ffma2_rn(make_float2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), al, make_float2(b.z, b.w));
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              v[j] = fmaf(__uint_as_float(r[j]), p.alpha, (p.bias != nullptr && col0 + j < p.N) ? __ldg(p.bias + col0 + j) : 0.f);
+            for (int j = 0; j < 32; j += 2) {
+              const float b0 = (p.bias != nullptr && col0 + j < p.N) ? __ldg(p.bias + col0 + j) : 0.f;
+              const float b1 = (p.bias != nullptr && col0 + j + 1 < p.N) ? __ldg(p.bias + col0 + j + 1) : 0.f;
+              v2[j >> 1] = __ffma2_rn(make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), al, make_float2(b0, b1));
+            }
           }
           uint8_t* slab_pre = slab_base + slab_sel * SLAB_BYTES;
           uint8_t* slab_act = slab_pre + SLAB_BYTES / 2;
@@ -463,11 +468,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               // out2 receives gelu'(pre): backward (EPI_DGELU) only ever needs the derivative, never pre itself
-              float g0, d0, g1, d1;
-              gelu_and_grad(v[c4 * 8 + 2 * t], g0, d0);
-              gelu_and_grad(v[c4 * 8 + 2 * t + 1], g1, d1);
-              pp[t] = pack_bf16x2(d0, d1);
-              pa[t] = pack_bf16x2(g0, g1);
+              float2 g, d;
+              gelu_and_grad2(v2[c4 * 4 + t], g, d);
+              pp[t] = pack_bf16x2(d.x, d.y);
+              pa[t] = pack_bf16x2(g.x, g.y);
             }
             const uint32_t off = lane * 64 + ((c4 ^ ((lane >> 1) & 3)) << 4);
             if (p.out2 != nullptr) *reinterpret_cast<uint4*>(slab_pre + off) = qp;

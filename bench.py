@@ -42,8 +42,11 @@ WORKLOADS = {
     "bert-base_s64_b8_n1": (BERT_BASE, 8, 1, 64),                # configs[0] shape
     "roberta-large_s256_b64_n15": (ROBERTA_LARGE, 64, 15, 256),  # configs[3] (needs activation chunking, see below)
 }
-# sequences per activation chunk of the context encoder (0 = keep everything): configs[3] would need ~214 GB otherwise
-ACT_CHUNK = {"roberta-large_s256_b64_n15": 256}
+# configs[3] (RoBERTa-large, 278 528 tokens x 24 layers per GPU) needs ~214 GB of saved activations in the full mode:
+# it runs with LEAN activations (22 KB instead of 32 KB per token and layer; gelu / gelu' / attention output rebuilt in
+# backward), which fits 180 GB without recomputing the forward.  --act-chunk N selects the older chunked-recompute path.
+ACT_CHUNK = {}
+LEAN = {"roberta-large_s256_b64_n15"}
 
 
 def flops_per_token_train(cfg, S):
@@ -456,6 +459,8 @@ def run_b200(args, workload):
         trainer.attach(task, None, "fit")
     task.train()
     task.context_encoder.activation_chunk = ACT_CHUNK.get(workload, 0) if args.act_chunk < 0 else args.act_chunk
+    lean = (workload in LEAN and task.context_encoder.activation_chunk == 0) or args.lean
+    task.context_encoder.lean_activations = task.query_encoder.lean_activations = lean
     host_batch = synth_batch(rank, cfg, B, n, S)
     dev_batch = to_device(host_batch, dev)
     lib = _lib.load()
@@ -575,6 +580,7 @@ def run_b200(args, workload):
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload, "model": ("BERT-base" if cfg is BERT_BASE else "RoBERTa-large") + " x2 (query+context, shared_model=false)",
                    "activation_chunk": ACT_CHUNK.get(workload, 0) if args.act_chunk < 0 else args.act_chunk,
+                   "lean_activations": bool(lean),
                    "queries_per_gpu": B, "hard_negatives": n, "contexts_per_gpu": B * (1 + n), "seq_len": S,
                    "global_batch": pairs_step, "parallelism": f"dp{world}", "negatives": "global in-batch" if world > 1 else "in-batch",
                    "optimizer": "fused AdamW + clip 2.0 + LambdaLR", "dropout": args.dropout,
@@ -644,6 +650,7 @@ def main():
     ap.add_argument("--no-selfcheck", action="store_true", help="skip the NCCL parity self-check at N > 1")
     ap.add_argument("--grad-dtype", default="fp32", choices=["fp32", "bf16"],
                     help="gradient all-reduce precision at N > 1 (fp32 = the reference default fp16_grads=false)")
+    ap.add_argument("--lean", action="store_true", help="lean activations (save_for_backward = 2) whatever the workload")
     ap.add_argument("--act-chunk", type=int, default=-1, help="override the activation chunk (sequences) of the context encoder")
     args = ap.parse_args()
     if args.impl == "reference":

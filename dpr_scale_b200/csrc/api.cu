@@ -90,6 +90,9 @@ int dprb_dropout_mask(uint8_t* keep, int64_t rows, int cols, float dropout_p, ui
                       int site, dprb_stream_t stream) {
   return dropout_mask(keep, rows, cols, dropout_p, dropout_seed, layer, site, S(stream));
 }
+int dprb_gelu_from_pre(const void* pre, void* out, int64_t n, dprb_stream_t stream) {
+  return gelu_from_pre(pre, out, n, S(stream));
+}
 int dprb_colsum_bf16(const void* x, int64_t ld, float* out, int T, int N, dprb_stream_t stream) {
   return colsum_bf16(x, ld, out, T, N, S(stream));
 }

@@ -29,6 +29,7 @@ int ln_bwd(const void* dy, const float* dy_cls, int cls_stride, const void* z, c
 int dropout_mask(uint8_t* out, long long rows, int cols, float p, unsigned long long seed, int layer, int site,
                  cudaStream_t stream);
 unsigned long long drop_site_seed(unsigned long long seed, int layer, int site);
+int gelu_from_pre(const void* pre, void* out, long long n, cudaStream_t stream);
 int colsum_bf16(const void* x, long long ld, float* out, int T, int N, cudaStream_t stream);
 
 int attn_fwd_lse(const void* qkv, const int32_t* attn_mask, void* ctx, float* lse, int nseq, int S, int heads,

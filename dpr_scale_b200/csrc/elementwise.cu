@@ -379,6 +379,24 @@ colsum_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ out,
   }
 }
 
+// hact = gelu(pre) over a flat bf16 array (8 elements per thread): the "lean activations" backward rebuilds the GELU
+// output it did not save, as the operand of the FFN-out weight gradient.
+__global__ void __launch_bounds__(256)
+gelu_from_pre_kernel(const bf16* __restrict__ pre, bf16* __restrict__ out, long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 q = ldg_nc_v4(pre + i * 8);
+    const uint32_t in[4] = {q.x, q.y, q.z, q.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float2 g, d;
+      gelu_and_grad2(unpack_bf16x2(in[t]), g, d);
+      o[t] = pack_bf16x2(g.x, g.y);
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 int grid_for_rows(int T) {
   int sms = num_sms();
   if (sms <= 0) sms = 148;
@@ -508,6 +526,19 @@ int colsum_bf16(const void* x, long long ld, float* out, int T, int N, cudaStrea
   row_chunks = (T + rows_per_cta - 1) / rows_per_cta;
   dim3 grid(col_blocks, row_chunks);
   colsum_kernel<<<grid, THREADS, 0, stream>>>((const bf16*)x, ld, out, T, N, rows_per_cta);
+  DPRB_LAUNCH_CHECK();
+  return 0;
+}
+
+int gelu_from_pre(const void* pre, void* out, long long n, cudaStream_t stream) {
+  DPRB_REQUIRE(n % 8 == 0 && ((reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+               "gelu_from_pre: n %% 8 == 0 and 16-byte aligned buffers required");
+  if (n == 0) return 0;
+  int sms = num_sms();
+  if (sms <= 0) sms = 148;
+  const long long n8 = n / 8;
+  const long long want = (n8 + 255) / 256;
+  gelu_from_pre_kernel<<<(int)(want < (long long)sms * 8 ? want : (long long)sms * 8), 256, 0, stream>>>((const bf16*)pre, (bf16*)out, n8);
   DPRB_LAUNCH_CHECK();
   return 0;
 }

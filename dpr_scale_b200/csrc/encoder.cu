@@ -30,6 +30,8 @@ struct LayerActs {
 
 struct Workspace {
   bf16 *rA, *rB;   // fp16 residual-stream copies of the LayerNorm outputs (forward only, not saved)
+  bf16 *ctx_t, *hact_t;  // lean mode: ONE attention-output / GELU-output buffer shared by all layers (rebuilt in backward)
+  int lean;
   bf16* x0;
   float* emb_stats;
   int n_layer_slots;
@@ -50,16 +52,19 @@ int plan(const dprb_encoder_weights* w, int nseq, int S, int save, void* base, W
   ws->x0 = (bf16*)c.take(T * H * 2);
   ws->emb_stats = (float*)c.take(T * 2 * 4);
   ws->n_layer_slots = save ? w->layers : 2;
+  ws->lean = (save == 2);
+  ws->ctx_t = ws->lean ? (bf16*)c.take(T * H * 2) : nullptr;
+  ws->hact_t = ws->lean ? (bf16*)c.take(T * I * 2) : nullptr;
   for (int i = 0; i < ws->n_layer_slots; ++i) {
     LayerActs& a = ws->slot[i];
     a.qkv = (bf16*)c.take(T * 3 * H * 2);
-    a.ctx = (bf16*)c.take(T * H * 2);
+    a.ctx = ws->lean ? ws->ctx_t : (bf16*)c.take(T * H * 2);
     a.lse = (float*)c.take((long long)nseq * w->heads * S * 4);
     a.z1 = (bf16*)c.take(T * H * 2);
     a.stats1 = (float*)c.take(T * 2 * 4);
     a.x1 = (bf16*)c.take(T * H * 2);
-    a.hpre = save ? (bf16*)c.take(T * I * 2) : nullptr;
-    a.hact = (bf16*)c.take(T * I * 2);
+    a.hpre = save ? (bf16*)c.take(T * I * 2) : nullptr;     // gelu'(pre), or pre itself in lean mode
+    a.hact = ws->lean ? ws->hact_t : (bf16*)c.take(T * I * 2);
     a.z2 = (bf16*)c.take(T * H * 2);
     a.stats2 = (float*)c.take(T * 2 * 4);
     a.out = (bf16*)c.take(T * H * 2);
@@ -145,6 +150,7 @@ int encoder_fwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b, floa
   const bf16* x = ws.x0;
   const float dp = b->dropout_p;
   DPRB_REQUIRE(dp >= 0.f && dp < 1.f, "encoder_fwd: dropout_p %f out of range", dp);
+  const int GELU_EPI = DPRB_EPI_BIAS_GELU | (ws.lean ? DPRB_GEMM_SAVE_PRE : 0);
   for (int l = 0; l < L; ++l) {
     const LayerW lw = layer_w(w, l);
     LayerActs& a = ws.slot[b->save_for_backward ? l : (l & 1)];
@@ -181,8 +187,9 @@ int encoder_bwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b, cons
   Workspace ws;
   DPRB_REQUIRE(b->save_for_backward, "encoder_bwd: forward was run without save_for_backward");
   DPRB_REQUIRE(w->grads != nullptr, "encoder_bwd: grads arena is NULL");
-  TRY(plan(w, b->nseq, b->S, 1, b->workspace, &ws));
+  TRY(plan(w, b->nseq, b->S, b->save_for_backward, b->workspace, &ws));
   DPRB_REQUIRE(b->workspace != nullptr && b->workspace_bytes >= ws.bytes, "encoder_bwd: workspace too small");
+  const int DGELU_EPI = ws.lean ? DPRB_EPI_DGELU_PRE : DPRB_EPI_DGELU;
   const int T = b->nseq * b->S, H = w->hidden, I = w->inter, L = w->layers;
   DPRB_REQUIRE(0 <= layer_lo && layer_lo < layer_hi && layer_hi <= L, "encoder_bwd: bad layer range [%d,%d)", layer_lo, layer_hi);
   if (T == 0) return 0;
@@ -199,7 +206,7 @@ int encoder_bwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b, cons
       TRY(ln_bwd(nullptr, dpooled, 1, a.z2, a.stats2, lw.ln2g, ws.gB, lw.g_ln2g, lw.g_ln2b, lw.g_b2, R, H, ws.gB2, dp,
                  site_seed_cls(b, l, DROP_SITE_FFN_OUT), RS_F16, stream));
       TRY(gemm_bf16(gLin, a.hact, lw.g_w2, H, I, R, H, I, I, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, 0.f, 0, stream));
-      TRY(gemm_bf16(gLin, lw.w2, ws.gH, R, I, H, H, I, I, 0, 1, DPRB_EPI_DGELU, nullptr, a.hpre, I, nullptr, 1.f, 1, lw.g_b1, 0.f, 0, stream));
+      TRY(gemm_bf16(gLin, lw.w2, ws.gH, R, I, H, H, I, I, 0, 1, DGELU_EPI, nullptr, a.hpre, I, nullptr, 1.f, 1, lw.g_b1, 0.f, 0, stream));
       TRY(gemm_bf16(ws.gH, a.x1, lw.g_w1, I, H, R, I, H, H, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, 0.f, 0, stream));
       TRY(gemm_bf16(ws.gH, lw.w1, ws.gA, R, H, I, I, H, H, 0, 1, DPRB_EPI_BIAS_RESIDUAL, nullptr, ws.gB, H, nullptr, 1.f, 1, nullptr, 0.f, 0, stream));
       TRY(ln_bwd(ws.gA, nullptr, 1, a.z1, a.stats1, lw.ln1g, ws.gB, lw.g_ln1g, lw.g_ln1b, lw.g_bo, R, H, ws.gB2, dp,
@@ -217,10 +224,12 @@ int encoder_bwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b, cons
     // LN2 backward (+ db2)
     TRY(ln_bwd(last ? nullptr : ws.gA, last ? dpooled : nullptr, b->S, a.z2, a.stats2, lw.ln2g, ws.gB, lw.g_ln2g,
                lw.g_ln2b, lw.g_b2, T, H, ws.gB2, dp, site_seed(b, l, DROP_SITE_FFN_OUT), RS_F16, stream));
+    // lean activations: the GELU output was not kept - rebuild it from the saved pre-activation
+    if (ws.lean) TRY(gelu_from_pre(a.hpre, a.hact, (long long)T * I, stream));
     // dW2 += dz2^T hact
     TRY(gemm_bf16(gLin, a.hact, lw.g_w2, H, I, T, H, I, I, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, 0.f, 0, stream));
     // dhpre = (dz2 W2) * gelu'(hpre)
-    TRY(gemm_bf16(gLin, lw.w2, ws.gH, T, I, H, H, I, I, 0, 1, DPRB_EPI_DGELU, nullptr, a.hpre, I, nullptr, 1.f, 1, lw.g_b1, 0.f, 0, stream));
+    TRY(gemm_bf16(gLin, lw.w2, ws.gH, T, I, H, H, I, I, 0, 1, DGELU_EPI, nullptr, a.hpre, I, nullptr, 1.f, 1, lw.g_b1, 0.f, 0, stream));
     // (db1 = column sums of dhpre is fused into that epilogue: +58 us vs 129 us for a separate streaming pass)
     // dW1 += dhpre^T x1
     TRY(gemm_bf16(ws.gH, a.x1, lw.g_w1, I, H, T, I, H, H, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, 0.f, 0, stream));
@@ -229,6 +238,8 @@ int encoder_bwd(const dprb_encoder_weights* w, const dprb_encoder_batch* b, cons
     // LN1 backward (+ dbo)
     TRY(ln_bwd(ws.gA, nullptr, 1, a.z1, a.stats1, lw.ln1g, ws.gB, lw.g_ln1g, lw.g_ln1b, lw.g_bo, T, H, ws.gB2, dp,
                site_seed(b, l, DROP_SITE_ATTN_OUT), RS_F16, stream));
+    // lean activations: the attention output was not kept - one more attention forward (same dropout stream)
+    if (ws.lean) TRY(attn_fwd_lse(a.qkv, b->attn_mask, a.ctx, a.lse, b->nseq, b->S, w->heads, dp, site_seed(b, l, DROP_SITE_ATTN), stream));
     // dWo += dz1^T ctx
     TRY(gemm_bf16(gLin, a.ctx, lw.g_wo, H, H, T, H, H, H, 1, 1, DPRB_EPI_F32_ATOMIC_ADD, nullptr, nullptr, 0, nullptr, 1.f, 0, nullptr, 0.f, 0, stream));
     // dctx = dz1 Wo

@@ -69,6 +69,7 @@ struct GemmParams {
   uint32_t idesc;      // UMMA instruction descriptor (operand formats: bf16 or fp16 per operand)
   int dynamic;         // 1: work units are handed out by cluster launch control (see below); 0: static striding
   int aux_f16, out_f16;  // aux / D hold fp16 instead of bf16 (the encoder's fp16 residual stream)
+  int save_pre;          // EPI_BIAS_GELU: out2 receives the pre-activation itself instead of gelu'(pre) (lean activations)
 };
 
 // ---- cluster / 2-CTA helpers -------------------------------------------------------------------------------
@@ -352,7 +353,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t* slab_base = smem_stage + ew * NSLAB * SLAB_BYTES;
     int slab_sel = 0;
     const bool f32_out = (p.epilogue == DPRB_EPI_F32_ATOMIC_ADD || p.epilogue == DPRB_EPI_F32_STORE);
-    const bool has_aux = (p.epilogue == DPRB_EPI_BIAS_RESIDUAL || p.epilogue == DPRB_EPI_DGELU);
+    const bool has_aux = (p.epilogue == DPRB_EPI_BIAS_RESIDUAL || p.epilogue == DPRB_EPI_DGELU || p.epilogue == DPRB_EPI_DGELU_PRE);
     const bool is_gelu = (p.epilogue == DPRB_EPI_BIAS_GELU);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -470,6 +471,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               // out2 receives gelu'(pre): backward (EPI_DGELU) only ever needs the derivative, never pre itself
               float2 g, d;
               gelu_and_grad2(v2[c4 * 4 + t], g, d);
+              if (p.save_pre) d = v2[c4 * 4 + t];        // lean activations: keep pre, rebuild gelu / gelu' in backward
               pp[t] = pack_bf16x2(d.x, d.y);
               pa[t] = pack_bf16x2(g.x, g.y);
             }
@@ -548,10 +550,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const bool af = p.aux_f16 != 0;
                 const float2 f0 = unpack_16x2(q.x, af), f1 = unpack_16x2(q.y, af), f2 = unpack_16x2(q.z, af), f3 = unpack_16x2(q.w, af);
                 const float a[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+                if (p.epilogue == DPRB_EPI_DGELU_PRE) {
+                  // aux holds the pre-activation: derivative rebuilt here (same fitted function as the forward)
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                  if (p.epilogue == DPRB_EPI_BIAS_RESIDUAL) v[c4 * 8 + t] += a[t];
-                  else v[c4 * 8 + t] *= a[t];  // EPI_DGELU: aux holds gelu'(pre) written by the forward epilogue
+                  for (int t = 0; t < 8; t += 2) {
+                    float2 g, d;
+                    gelu_and_grad2(make_float2(a[t], a[t + 1]), g, d);
+                    v[c4 * 8 + t] *= d.x; v[c4 * 8 + t + 1] *= d.y;
+                  }
+                } else {
+#pragma unroll
+                  for (int t = 0; t < 8; ++t) {
+                    if (p.epilogue == DPRB_EPI_BIAS_RESIDUAL) v[c4 * 8 + t] += a[t];
+                    else v[c4 * 8 + t] *= a[t];  // EPI_DGELU: aux holds gelu'(pre) written by the forward epilogue
+                  }
                 }
               }
             }
@@ -685,7 +697,7 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long l
               long long ld_aux, void* out2, float alpha, int splits, float* colsum, float dropout_p,
               unsigned long long drop_site_seed, cudaStream_t stream) {
   DPRB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
-  const int dt_flags = epilogue & ~0xFF;   // DPRB_GEMM_{A,B,AUX,OUT}_F16
+  const int dt_flags = epilogue & ~0xFF;   // DPRB_GEMM_{A,B,AUX,OUT}_F16, DPRB_GEMM_SAVE_PRE
   epilogue &= 0xFF;
   const int a_f16 = (dt_flags & DPRB_GEMM_A_F16) != 0, b_f16 = (dt_flags & DPRB_GEMM_B_F16) != 0;
   const int aux_f16 = (dt_flags & DPRB_GEMM_AUX_F16) != 0, out_f16 = (dt_flags & DPRB_GEMM_OUT_F16) != 0;
@@ -700,7 +712,7 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long l
                "gemm: bf16 output must be 16-byte aligned with ldd %% 8 == 0 (ldd=%lld)", ldd);
   DPRB_REQUIRE(!f32_out || (ldd % 4 == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0),
                "gemm: fp32 output must be 16-byte aligned with ldd %% 4 == 0 (ldd=%lld)", ldd);
-  if (epilogue == DPRB_EPI_BIAS_RESIDUAL || epilogue == DPRB_EPI_DGELU)
+  if (epilogue == DPRB_EPI_BIAS_RESIDUAL || epilogue == DPRB_EPI_DGELU || epilogue == DPRB_EPI_DGELU_PRE)
     DPRB_REQUIRE(aux != nullptr && ld_aux % 8 == 0, "gemm: epilogue %d needs aux with ld %% 8 == 0", epilogue);
   if (bias != nullptr) DPRB_REQUIRE((reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm: bias not 16B aligned");
 
@@ -745,6 +757,7 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long l
   p.out2 = reinterpret_cast<bf16*>(out2); p.alpha = alpha;
   p.colsum = colsum;
   p.aux_f16 = aux_f16; p.out_f16 = out_f16;
+  p.save_pre = (dt_flags & DPRB_GEMM_SAVE_PRE) != 0;
   p.idesc = make_idesc_16_f32(CTA_M * CG, BLOCK_N, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, a_f16, b_f16);
   p.drop = drop_from_site(epilogue == DPRB_EPI_BIAS_RESIDUAL ? dropout_p : 0.f, drop_site_seed);
   static const bool no_aux_pf = (std::getenv("DPRB_NO_AUX_PF") != nullptr);

@@ -358,6 +358,10 @@ class HFEncoder(nn.Module):
         self._drop_calls = 0
         # sequences per activation chunk (0 = keep all activations of the batch; see _ChunkedEncoderFn)
         self.activation_chunk = int(os.environ.get("DPRB_ACTIVATION_CHUNK", "0"))
+        # lean activations (dprb_encoder_batch.save_for_backward = 2): keep the FFN pre-activation instead of
+        # gelu + gelu' and no attention output; backward rebuilds them (one elementwise pass + one attention forward per
+        # layer).  22 KB instead of 32 KB per token and layer at RoBERTa-large: BASELINE config 4 fits without recompute.
+        self.lean_activations = bool(int(os.environ.get("DPRB_LEAN_ACTIVATIONS", "0")))
 
     # ------------------------------------------------------------------ construction helpers
     @classmethod
@@ -469,9 +473,12 @@ class HFEncoder(nn.Module):
         w.grads = t._grads.data_ptr() if (with_grads and t._grads is not None) else None
         return w
 
+    def _save_mode(self, save):
+        return 0 if not save else (2 if self.lean_activations else 1)
+
     def _workspace(self, nseq, S, save):
         w = self._weights_struct(False)
-        nbytes = _lib.load().dprb_encoder_workspace_bytes(ctypes.byref(w), nseq, S, int(save))
+        nbytes = _lib.load().dprb_encoder_workspace_bytes(ctypes.byref(w), nseq, S, self._save_mode(save))
         if nbytes < 0:
             check(1, "dprb_encoder_workspace_bytes")
         if save:
@@ -517,7 +524,7 @@ class HFEncoder(nn.Module):
         b.ids, b.type_ids, b.pos_ids = ids.data_ptr(), tt.data_ptr(), pos.data_ptr()
         b.attn_mask = am.data_ptr() if am is not None else None
         b.workspace, b.workspace_bytes = base, ws.numel() - (base - ws.data_ptr())
-        b.save_for_backward = int(save)
+        b.save_for_backward = self._save_mode(save)
         # HF applies dropout only in train mode; the seed changes every forward and is replayed by backward
         use_drop = (self.training and save) if train_dropout is None else (self.training and train_dropout)
         b.dropout_p = self.dropout if use_drop else 0.0

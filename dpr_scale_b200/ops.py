@@ -8,7 +8,8 @@ import torch
 from . import _lib
 from ._lib import check
 
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_DGELU, EPI_F32_ATOMIC_ADD, EPI_F32_STORE = range(6)
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_DGELU, EPI_F32_ATOMIC_ADD, EPI_F32_STORE, EPI_DGELU_PRE = range(7)
+GEMM_SAVE_PRE = 0x1000
 # OR-ed into the epilogue: that operand holds fp16 instead of bf16 (include/dprb.h DPRB_GEMM_*_F16)
 GEMM_A_F16, GEMM_B_F16, GEMM_AUX_F16, GEMM_OUT_F16 = 0x100, 0x200, 0x400, 0x800
 
@@ -112,6 +113,12 @@ def dropout_mask(rows, cols, p, seed, layer, site, device="cuda"):
     out = torch.empty(rows, cols, dtype=torch.uint8, device=device)
     check(_lib.load().dprb_dropout_mask(_ptr(out), rows, cols, float(p), int(seed), layer, site, _stream()),
           "dprb_dropout_mask")
+    return out
+
+
+def gelu_from_pre(pre):
+    out = torch.empty_like(pre)
+    check(_lib.load().dprb_gelu_from_pre(_ptr(pre), _ptr(out), pre.numel(), _stream()), "dprb_gelu_from_pre")
     return out
 
 

@@ -56,14 +56,18 @@ enum {
   DPRB_EPI_DGELU = 3,          /* D(bf16) = acc * aux(bf16), aux = the gelu' saved by BIAS_GELU          */
   DPRB_EPI_F32_ATOMIC_ADD = 4, /* D(fp32) += acc  (split-K over `splits` CTAs; 0 = choose)            */
   DPRB_EPI_F32_STORE = 5,      /* D(fp32) = acc + bias                                                 */
-  DPRB_EPI_COUNT = 6
+  DPRB_EPI_DGELU_PRE = 6,      /* D(bf16) = acc * gelu'(aux), aux(bf16) = the PRE-activation saved by BIAS_GELU|SAVE_PRE */
+  DPRB_EPI_COUNT = 7
 };
 /* OR-ed into `epilogue`: the named 16-bit operand holds IEEE fp16 instead of bf16 (tcgen05 kind::f16 takes either
  * format per operand).  The encoder keeps its residual stream - LayerNorm inputs and outputs - in fp16 (11 significand
  * bits in the same 2 bytes): these are the tensors HF's autocast keeps in fp32 (modeling_bert.py:296-298, :354-356
  * run LayerNorm and the residual add outside the 16-bit region).  AUX / OUT apply to the BIAS and BIAS_RESIDUAL
  * epilogues. */
-enum { DPRB_GEMM_A_F16 = 0x100, DPRB_GEMM_B_F16 = 0x200, DPRB_GEMM_AUX_F16 = 0x400, DPRB_GEMM_OUT_F16 = 0x800 };
+enum { DPRB_GEMM_A_F16 = 0x100, DPRB_GEMM_B_F16 = 0x200, DPRB_GEMM_AUX_F16 = 0x400, DPRB_GEMM_OUT_F16 = 0x800,
+       /* BIAS_GELU: out2 receives the pre-activation instead of gelu'(pre) - the "lean activations" mode of the encoder,
+        * which saves ONE [T, I] tensor per layer (pre) instead of two (gelu', gelu) and rebuilds both in backward. */
+       DPRB_GEMM_SAVE_PRE = 0x1000 };
 /* (A_F16 and B_F16 must be given together: the hardware rejects an fp16 x bf16 operand pair.) */
 int dprb_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int64_t lda, int64_t ldb,
                    int64_t ldd, int a_mn_major, int b_mn_major, int epilogue, const float* bias,
@@ -121,6 +125,9 @@ uint64_t dprb_dropout_site_seed(uint64_t dropout_seed, int layer, int site);
 int dprb_dropout_mask(uint8_t* keep, int64_t rows, int cols, float dropout_p, uint64_t dropout_seed, int layer,
                       int site, dprb_stream_t stream);
 
+/* out(bf16) = gelu(pre(bf16)), elementwise over n (multiple of 8) values: rebuilds BertIntermediate's activation
+ * (modeling_bert.py:339-342) in backward when the encoder ran with lean activations (save_for_backward = 2). */
+int dprb_gelu_from_pre(const void* pre_bf16, void* out_bf16, int64_t n, dprb_stream_t stream);
 /* Column sums: out[n] += sum_t x[t, n]  (bias gradients; x bf16 [T, N] with leading dim ld). */
 int dprb_colsum_bf16(const void* x_bf16, int64_t ld, float* out, int T, int N, dprb_stream_t stream);
 
@@ -225,7 +232,13 @@ typedef struct {
   /* activation workspace, caller-allocated: see dprb_encoder_workspace_bytes */
   void* workspace;
   int64_t workspace_bytes;
-  int32_t save_for_backward; /* 0: forward-only (generate_embeddings path) reuses per-layer buffers */
+  int32_t save_for_backward; /* 0: forward-only (generate_embeddings path) reuses per-layer buffers; 1: keep every
+                              * activation backward reads; 2: "lean" - per layer keep qkv, the two pre-LayerNorm sums,
+                              * x1, the FFN pre-activation and the layer output, and REBUILD the attention output
+                              * (one more attention forward) and gelu / gelu' (from the pre-activation) in backward:
+                              * 22 KB instead of 32 KB per token and layer at RoBERTa-large, which is what lets
+                              * BASELINE config 4 (278 528 tokens x 24 layers per GPU) fit 180 GB without recomputing
+                              * the whole forward. */
   float dropout_p;           /* hidden + attention-probability dropout (HFEncoder's `dropout`); 0 in eval mode */
   uint64_t dropout_seed;     /* per-forward seed; backward must be given the same value */
 } dprb_encoder_batch;

@@ -113,6 +113,37 @@ def check_gemm_f16_stream(M=384, N=768, K=512, seed=30):
     return res
 
 
+def check_gemm_lean(M=384, N=512, K=256, seed=40):
+    """The lean-activations epilogues: BIAS_GELU | SAVE_PRE (out2 = pre-activation), DGELU_PRE (acc * gelu'(pre) rebuilt
+    from the saved pre-activation) and the elementwise gelu_from_pre - against erf-GELU and its exact derivative."""
+    g = torch.Generator().manual_seed(seed)
+    A = _bf(torch.randn(M, K, generator=g))
+    B = _bf(torch.randn(N, K, generator=g) * 0.2)
+    bias = torch.randn(N, generator=g)
+    res = {}
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    pre_d = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(A.to(DEV), B.to(DEV), out, M, N, K, K, K, N, False, False, ops.EPI_BIAS_GELU | ops.GEMM_SAVE_PRE, bias.to(DEV),
+             out2=pre_d)
+    pre = A.double() @ B.double().T + bias.double()
+    _close("lean_pre", pre_d, pre, 2 ** -7, 1e-3, res)
+    _close("lean_act", out, oenc.gelu_erf(pre), 2 ** -7, 1e-3, res)
+    _close("lean_gelu_from_pre", ops.gelu_from_pre(pre_d), oenc.gelu_erf(pre_d.double().cpu()), 2 ** -7, 1e-3, res)
+    # backward: dH[M, K2] = (dY W) * gelu'(pre) with B read MN-major; pre from the forward call above
+    dY = _bf(torch.randn(M, K, generator=g))
+    W = _bf(torch.randn(K, N, generator=g) * 0.2)          # [K_in = K, N_out = N] row-major == B(n, k) MN-major
+    dH = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    cs = torch.zeros(N, device=DEV)
+    ops.gemm(dY.to(DEV), W.to(DEV), dH, M, N, K, K, N, N, False, True, ops.EPI_DGELU_PRE, None, pre_d, N, colsum=cs)
+    x = pre_d.double().cpu()
+    cdf = 0.5 * (1 + torch.erf(x / math.sqrt(2)))
+    pdf = torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi)
+    want = (dY.double() @ W.double()) * (cdf + x * pdf)
+    _close("lean_dgelu", dH, want, 2 ** -7, 2e-3, res)
+    _close("lean_dgelu_colsum", cs, dH.double().cpu().sum(0), 1e-5, 1e-3, res)
+    return res
+
+
 # ------------------------------------------------------------------ LayerNorm / embeddings
 def check_ln(T=777, H=768, cls_stride=0, seed=1, f16=False):
     """f16: z arrives in fp16 (written by a DPRB_GEMM_OUT_F16 epilogue) and the fp16 residual copy y_res is requested."""
@@ -332,6 +363,8 @@ CHECKS = {
     "ln_128": lambda: check_ln(100, 128),
     "ln_768_f16": lambda: check_ln(777, 768, f16=True),
     "ln_1024_cls_f16": lambda: check_ln(512, 1024, cls_stride=64, f16=True),
+    "gemm_lean_epilogues": lambda: check_gemm_lean(),
+    "gemm_lean_epilogues_big": lambda: check_gemm_lean(1024, 3072, 768, seed=41),
     "gemm_f16_stream": lambda: check_gemm_f16_stream(),
     "gemm_f16_stream_big": lambda: check_gemm_f16_stream(1024, 768, 3072, seed=31),
     "embed": lambda: check_embed(),

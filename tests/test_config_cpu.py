@@ -182,3 +182,19 @@ def test_committed_bench_line_has_the_contract_keys():
     cb = line["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] > 0
     assert line["gpu_launches"] > 0 and set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+def test_dragon_and_slurm_configs_compose_like_the_reference():
+    """conf/dragon_aws.yaml (BASELINE config 4's recipe) and conf/trainer/slurm*.yaml mirror the reference's files of the
+    same names (values from /root/reference/dpr_scale/conf/dragon_aws.yaml:6-35, conf/trainer/slurm.yaml:5-15)."""
+    from dpr_scale_b200.utils.config import compose
+    cfg = compose("dragon_aws", ["datamodule.corpus_path=c.tsv", "datamodule.train_path=[a.jsonl,b.jsonl]",
+                                 "datamodule.val_path=d.jsonl", "datamodule.test_path=d.jsonl", "task.model.model_path=/m"])
+    assert cfg.datamodule._target_.endswith("DenseRetrieverMultiJsonlDataModule")
+    assert cfg.datamodule.train_path == ["a.jsonl", "b.jsonl"] and cfg.datamodule.batch_size == 64
+    assert cfg.datamodule.num_negative == 1 and cfg.datamodule.pos_ctx_sample is True and cfg.datamodule.num_test_negative == 50
+    assert cfg.task.optim.lr == 3e-5 and cfg.task.warmup_steps == 10000 and cfg.task.shared_model is False
+    assert cfg.trainer.gpus == 8 and cfg.trainer.num_nodes == 4 and cfg.trainer.max_epochs == 20 and cfg.trainer.strategy == "ddp"
+    assert cfg.trainer.gradient_clip_val == 2.0 and cfg.trainer.precision == 16
+    s = compose("config", ["trainer=slurm", "task.model.model_path=/m"])
+    assert s.trainer.strategy == "ddp_sharded" and s.trainer.gpus == 8 and s.trainer.max_epochs == 25

@@ -78,7 +78,7 @@ __device__ __forceinline__ void row_stats(const float (&x)[MAXC][8], const bool 
 
 // ------------------------------------------------------------------ LayerNorm forward
 template <int MAXC, bool EMBED>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 4)
 ln_fwd_kernel(const bf16* __restrict__ z, const int64_t* __restrict__ ids, const int64_t* __restrict__ tts,
               const int64_t* __restrict__ pids, const float* __restrict__ word, const float* __restrict__ pos,
               const float* __restrict__ type, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -88,17 +88,18 @@ ln_fwd_kernel(const bf16* __restrict__ z, const int64_t* __restrict__ ids, const
   // next residual add reads (tcgen05 kind::f16 cannot mix an fp16 operand with bf16 weights, so the stream that must
   // stay precise travels beside the GEMM operand instead of replacing it).  z_f16: the input sum holds fp16.
   const bool f16 = z_f16 != 0;
+  // gamma / beta live in shared memory (8 KB at H = 1024), not in 48 registers per thread: at 110 registers only two
+  // 8-warp CTAs fit an SM and 16 rows in flight leave the kernel latency-bound (ncu r2: 3.4 TB/s); at ~64 registers
+  // four CTAs are resident.
+  __shared__ __align__(16) float s_gb[2 * 1024];
+  for (int i = threadIdx.x; i < H; i += THREADS) { s_gb[i] = gamma[i]; s_gb[1024 + i] = beta[i]; }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * WARPS + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * WARPS;
   bool act[MAXC];
-  float g[MAXC][8], b[MAXC][8];
 #pragma unroll
-  for (int i = 0; i < MAXC; ++i) {
-    const int c = (lane + 32 * i) * 8;
-    act[i] = c < H;
-    if (act[i]) { load8f(gamma + c, g[i]); load8f(beta + c, b[i]); }
-  }
+  for (int i = 0; i < MAXC; ++i) act[i] = (lane + 32 * i) * 8 < H;
   for (int row = warp_global; row < T; row += nwarps) {
     float x[MAXC][8];
     if (EMBED) {
@@ -134,9 +135,11 @@ ln_fwd_kernel(const bf16* __restrict__ z, const int64_t* __restrict__ ids, const
     for (int i = 0; i < MAXC; ++i) {
       const int c = (lane + 32 * i) * 8;
       if (act[i]) {
-        float o[8];
+        float o[8], g8[8], b8[8];
+        load8f(s_gb + c, g8);
+        load8f(s_gb + 1024 + c, b8);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (x[i][j] - mean) * rstd * g[i][j] + b[i][j];
+        for (int j = 0; j < 8; ++j) o[j] = (x[i][j] - mean) * rstd * g8[j] + b8[j];
         if (EMBED && drop.on()) {  // embedding dropout (modeling_bert.py:111)
 #pragma unroll
           for (int j = 0; j < 8; j += 2) {

@@ -20,8 +20,6 @@ WANT = {
     "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_throughput_pct",
     "sm__warps_active.avg.pct_of_peak_sustained_active": "achieved_occupancy_pct",
     "launch__registers_per_thread": "registers",
-    "launch__grid_size": "grid",
-    "launch__block_size": "block",
     "launch__shared_mem_per_block_dynamic": "dyn_smem_bytes",
     "lts__t_sector_hit_rate.pct": "l2_hit_pct",
     "sm__cycles_active.avg": "sm_cycles_active_avg",
@@ -48,11 +46,13 @@ def main():
     col = {h: i for i, h in enumerate(hdr)}
     out = []
     launches = [r for r in rows[2:] if len(r) == len(hdr)]
-    # kernel_zoo launches helper kernels of torch too (randn, fill...): keep only dprb kernels, in order
-    ours = [r for r in launches if "dprb::" in r[col["Kernel Name"]]]
+    # the capture is restricted to the library's kernels with ncu's -k regex, in launch order
+    ours = launches
     for i, r in enumerate(ours):
         rec = {"launch": i, "role": names[i] if i < len(names) else None,
-               "kernel": re.sub(r"\(.*", "", r[col["Kernel Name"]].replace("dprb::<unnamed>::", "").replace("void ", ""))}
+               "kernel": re.sub(r"\(CUtensorMap.*|\((const |float|unsigned|__nv|long).*", "",
+                                r[col["Kernel Name"]].replace("dprb::<unnamed>::", "").replace("unnamed>::", "").replace("void ", "")),
+               "grid": r[col["Grid Size"]], "block": r[col["Block Size"]]}
         for k, nm in WANT.items():
             if k in col:
                 v = num(r[col[k]])

@@ -62,3 +62,81 @@ def test_two_rank_global_negatives_match_reference():
         assert abs(loss - want) <= 5e-2, (loss, want)
         assert grel <= 1.5 * amp, (grel, amp)
     assert abs(ret[0][0] - ret[1][0]) < 1e-6  # every rank computes the same global loss
+
+
+def _shared_worker(rank, world, port, ret):
+    """shared_model=True (the reference's constructor default) on 2 ranks: ONE encoder back-propagates twice per step into
+    one gradient arena; the bucketed all-reduce must reduce every slice exactly once (it used to reduce twice).
+    Reference semantics (dpr_task.py:163-195 + DDP): SUM over ranks of the per-rank gradients == gradient of the global
+    loss, i.e. what ONE process computes on the concatenated batch."""
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from dpr_scale_b200.task.dpr_task import DenseRetrieverTask
+    from dpr_scale_b200.trainer import Trainer
+    from tests.test_task_gpu import CFG, _batch
+    from tests.util import load_golden, rel_l2, sub
+    g2, g1 = load_golden("golden_2rank.npz"), load_golden("golden_1rank.npz")
+    T = float(g1["temperature"])
+
+    def make(distributed):
+        task = DenseRetrieverTask(transform={}, datamodule=None, shared_model=True, softmax_temperature=T,
+                                  model={"_target_": "dpr_scale_b200.models.hf_model.HFEncoder.from_config", "config": CFG,
+                                         "dropout": 0.0},
+                                  optim={"_target_": "dpr_scale_b200.optim.FusedAdamW", "lr": 0.0})
+        tr = Trainer(max_steps=10, gradient_clip_val=0.0, device=torch.device("cuda", rank), grad_bucket_layers=1)
+        if not distributed:
+            tr.world_size, tr.strategy = 1, None
+        tr.attach(task, None, "fit")
+        task.query_encoder.load_state_dict(sub(g1, "sd_q/"))
+        task.train()
+        return task, tr
+
+    task, tr = make(True)
+    assert task.query_encoder is task.context_encoder
+    batches = [_batch(g2, f"rank{r}/batch/") for r in range(world)]
+    tr.optimizer.zero_grad()
+    loss = task.training_step(batches[rank], 0)
+    loss.backward()
+    tr._allreduce_grads()
+    torch.cuda.synchronize()
+    got = task.query_encoder.grads.clone()
+    rel = -1.0
+    if rank == 0:
+        # single-process reference on the concatenated global batch (queries and contexts padded to a common length)
+        ref, rtr = make(False)
+        rtr.task.trainer = None
+
+        def cat(key):
+            parts = [b[key] for b in batches]
+            S = max(p["input_ids"].shape[1] for p in parts)
+            out = {}
+            for k in parts[0]:
+                out[k] = torch.cat([torch.nn.functional.pad(p[k], (0, S - p[k].shape[1])) for p in parts], 0)
+            return out
+        C = batches[0]["contexts_ids"]["input_ids"].shape[0]
+        big = {"query_ids": cat("query_ids"), "contexts_ids": cat("contexts_ids"),
+               "pos_ctx_indices": torch.cat([b["pos_ctx_indices"] + i * C for i, b in enumerate(batches)]),
+               "ctx_mask": torch.cat([b["ctx_mask"] for b in batches])}
+        ref.query_encoder.zero_grad()
+        rloss = ref.training_step(big, 0)
+        rloss.backward()
+        torch.cuda.synchronize()
+        rel = rel_l2(got, ref.query_encoder.grads)
+        ret["loss"] = (float(loss), float(rloss))
+    ret[rank] = rel
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_shared_model_gradients_reduced_once():
+    import torch.multiprocessing as mp
+    ret = mp.Manager().dict()
+    mp.spawn(_shared_worker, args=(2, 29657, ret), nprocs=2, join=True)
+    loss, rloss = ret["loss"]
+    assert abs(loss - rloss) <= 2e-3, (loss, rloss)
+    # the double all-reduce gave W * sum_ctx + sum_q: a relative error of order 1; bf16 / atomics noise is ~1e-2
+    assert 0 <= ret[0] <= 3e-2, ret[0]

@@ -197,6 +197,11 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ dy_cls, int
   const int nwarps = gridDim.x * WARPS;
   bool act[MAXC];
   float g[MAXC][8], ag[MAXC][8], ab[MAXC][8], az[MAXC][8], az1[MAXC][8];
+  // EMBED: position-table gradient of the position this warp is currently seeing.  With absolute positions
+  // (pos = token index mod S) and a warp stride that is a multiple of S - the common case - every row of a warp has
+  // the SAME position, so its 1 024-way contended atomics (131 072 tokens onto 128 rows) become one flush per warp.
+  float apos[EMBED ? MAXC : 1][8];
+  long long cur_pp = -1;
 #pragma unroll
   for (int i = 0; i < MAXC; ++i) {
     const int c = (lane + 32 * i) * 8;
@@ -204,7 +209,24 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ dy_cls, int
     if (act[i]) load8f(gamma + c, g[i]);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { ag[i][j] = 0.f; ab[i][j] = 0.f; az[i][j] = 0.f; az1[i][j] = 0.f; }
+    if (EMBED) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) apos[i][j] = 0.f;
+    }
   }
+  auto flush_pos = [&]() {
+    if (EMBED && cur_pp >= 0) {
+#pragma unroll
+      for (int i = 0; i < MAXC; ++i)
+        if (act[i]) {
+          const int c = (lane + 32 * i) * 8;
+          red_add_v4_f32(dpos + cur_pp * H + c, apos[i][0], apos[i][1], apos[i][2], apos[i][3]);
+          red_add_v4_f32(dpos + cur_pp * H + c + 4, apos[i][4], apos[i][5], apos[i][6], apos[i][7]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) apos[i][j] = 0.f;
+        }
+    }
+  };
   // Dense path: each lane stages its own 16-byte chunks of the next PF_DEPTH rows in shared memory with cp.async
   // (a per-lane FIFO: no cross-lane visibility needed), so PF_DEPTH rows of dy and z are in flight per warp —
   // at one 8-warp CTA per SM (register-bound) a single row in flight leaves the kernel latency-bound at ~2.5 TB/s.
@@ -261,7 +283,10 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ dy_cls, int
     const float mean = dense_path ? pf_mean : stats[2 * (long long)row];
     const float rstd = dense_path ? pf_rstd : stats[2 * (long long)row + 1];
     long long id = 0, tt = 0, pp = 0;
-    if (EMBED) { id = ids[row]; tt = tts ? tts[row] : 0; pp = pids[row]; }
+    if (EMBED) {
+      id = ids[row]; tt = tts ? tts[row] : 0; pp = pids[row];
+      if (pp != cur_pp) { flush_pos(); cur_pp = pp; }    // warp-uniform
+    }
     float xh[MAXC][8], d[MAXC][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -315,10 +340,9 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ dy_cls, int
           // the atomic instructions of the scalar form); the (tiny) type table is accumulated in registers
           red_add_v4_f32(dword + id * H + c, o[0], o[1], o[2], o[3]);
           red_add_v4_f32(dword + id * H + c + 4, o[4], o[5], o[6], o[7]);
-          red_add_v4_f32(dpos + pp * H + c, o[0], o[1], o[2], o[3]);
-          red_add_v4_f32(dpos + pp * H + c + 4, o[4], o[5], o[6], o[7]);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
+            apos[EMBED ? i : 0][j] += o[j];
             if (tt == 0) az[i][j] += o[j];
             else if (tt == 1) az1[i][j] += o[j];
             else atomicAdd(dtype + tt * H + c + j, o[j]);
@@ -346,6 +370,7 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ dy_cls, int
     }
   }
   cp_async_wait<0>();
+  flush_pos();
   flush_cols<MAXC>(ag, act, smem_f, dgamma, H);
   flush_cols<MAXC>(ab, act, smem_f, dbeta, H);
   if (EMBED) {

@@ -77,7 +77,7 @@ __device__ __forceinline__ void row_stats(const float (&x)[MAXC][8], const bool 
 }
 
 // ------------------------------------------------------------------ LayerNorm forward
-template <int MAXC, bool EMBED>
+template <int MAXC, bool EMBED, bool ZF16>
 __global__ void __launch_bounds__(THREADS, 4)
 ln_fwd_kernel(const bf16* __restrict__ z, const int64_t* __restrict__ ids, const int64_t* __restrict__ tts,
               const int64_t* __restrict__ pids, const float* __restrict__ word, const float* __restrict__ pos,
@@ -87,7 +87,8 @@ ln_fwd_kernel(const bf16* __restrict__ z, const int64_t* __restrict__ ids, const
   // y: bf16 (the next GEMM's A operand, saved for wgrad).  y_res (optional): the same values in fp16 - the copy the
   // next residual add reads (tcgen05 kind::f16 cannot mix an fp16 operand with bf16 weights, so the stream that must
   // stay precise travels beside the GEMM operand instead of replacing it).  z_f16: the input sum holds fp16.
-  const bool f16 = z_f16 != 0;
+  constexpr bool f16 = ZF16;      // compile-time: a run-time format select costs two conversions + a select per pair
+  (void)z_f16;
   // gamma / beta live in shared memory (8 KB at H = 1024), not in 48 registers per thread: at 110 registers only two
   // 8-warp CTAs fit an SM and 16 rows in flight leave the kernel latency-bound (ncu r2: 3.4 TB/s); at ~64 registers
   // four CTAs are resident.
@@ -181,7 +182,7 @@ __device__ __forceinline__ void flush_cols(float (&acc)[MAXC][8], const bool (&a
   }
 }
 
-template <int MAXC, bool EMBED>
+template <int MAXC, bool EMBED, bool ZF16>
 __global__ void __launch_bounds__(THREADS)
 ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ dy_cls, int cls_stride,
               const bf16* __restrict__ z, const int64_t* __restrict__ ids, const int64_t* __restrict__ tts,
@@ -191,7 +192,8 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ dy_cls, int
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int T, int H,
               bf16* __restrict__ dzm, Drop drop, int z_f16) {
   extern __shared__ float smem_f[];
-  const bool zf16 = z_f16 != 0;   // the saved pre-LayerNorm sum z holds fp16 (gradients dy / dz stay bf16)
+  constexpr bool zf16 = ZF16;     // the saved pre-LayerNorm sum z holds fp16 (gradients dy / dz stay bf16)
+  (void)z_f16;
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * WARPS + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * WARPS;
@@ -459,7 +461,7 @@ int embed_ln_fwd(const int64_t* ids, const int64_t* type_ids, const int64_t* pos
   if (T == 0) return 0;
   (void)vocab; (void)max_pos; (void)type_vocab;
   const int grid = grid_for_rows(T);
-#define CALL(C) ln_fwd_kernel<C, true><<<grid, THREADS, 0, stream>>>(nullptr, ids, type_ids, pos_ids, word, pos, type, gamma, beta, (bf16*)y, (bf16*)y_res, stats, nullptr, 1, T, H, eps, drop, 0)
+#define CALL(C) ln_fwd_kernel<C, true, false><<<grid, THREADS, 0, stream>>>(nullptr, ids, type_ids, pos_ids, word, pos, type, gamma, beta, (bf16*)y, (bf16*)y_res, stats, nullptr, 1, T, H, eps, drop, 0)
   DISPATCH_MAXC(H, CALL);
 #undef CALL
   DPRB_LAUNCH_CHECK();
@@ -472,7 +474,11 @@ int ln_fwd(const void* z, const float* gamma, const float* beta, void* y, float*
   if (T == 0) return 0;
   DPRB_REQUIRE(cls_out == nullptr || cls_stride > 0, "ln_fwd: cls_stride must be positive");
   const int grid = grid_for_rows(T);
-#define CALL(C) ln_fwd_kernel<C, false><<<grid, THREADS, 0, stream>>>((const bf16*)z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, gamma, beta, (bf16*)y, (bf16*)y_res, stats, cls_out, cls_stride > 0 ? cls_stride : 1, T, H, eps, Drop{0u, 0u, 1.f, 1u}, z_f16)
+#define CALL(C)                                                                                                          \
+  do {                                                                                                                   \
+    if (z_f16) ln_fwd_kernel<C, false, true><<<grid, THREADS, 0, stream>>>((const bf16*)z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, gamma, beta, (bf16*)y, (bf16*)y_res, stats, cls_out, cls_stride > 0 ? cls_stride : 1, T, H, eps, Drop{0u, 0u, 1.f, 1u}, 1); \
+    else ln_fwd_kernel<C, false, false><<<grid, THREADS, 0, stream>>>((const bf16*)z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, gamma, beta, (bf16*)y, (bf16*)y_res, stats, cls_out, cls_stride > 0 ? cls_stride : 1, T, H, eps, Drop{0u, 0u, 1.f, 1u}, 0); \
+  } while (0)
   DISPATCH_MAXC(H, CALL);
 #undef CALL
   DPRB_LAUNCH_CHECK();
@@ -495,13 +501,18 @@ int ln_bwd(const void* dy, const float* dy_cls, int cls_stride, const void* z, c
   if (ring > smem) smem = ring;
   static bool attr = false;
   if (!attr) {
-    DPRB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    DPRB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    DPRB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    DPRB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+#define SET_ATTR(C)                                                                                                                       \
+    DPRB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<C, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
+    DPRB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<C, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    SET_ATTR(1) SET_ATTR(2) SET_ATTR(3) SET_ATTR(4)
+#undef SET_ATTR
     attr = true;
   }
-#define CALL(C) ln_bwd_kernel<C, false><<<grid, THREADS, smem, stream>>>((const bf16*)dy, dy_cls, cls_stride > 0 ? cls_stride : 1, (const bf16*)z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stats, gamma, (bf16*)dz, nullptr, nullptr, nullptr, dgamma, dbeta, dbias, T, H, (bf16*)dzm, drop, z_f16)
+#define CALL(C)                                                                                                          \
+  do {                                                                                                                   \
+    if (z_f16) ln_bwd_kernel<C, false, true><<<grid, THREADS, smem, stream>>>((const bf16*)dy, dy_cls, cls_stride > 0 ? cls_stride : 1, (const bf16*)z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stats, gamma, (bf16*)dz, nullptr, nullptr, nullptr, dgamma, dbeta, dbias, T, H, (bf16*)dzm, drop, 1); \
+    else ln_bwd_kernel<C, false, false><<<grid, THREADS, smem, stream>>>((const bf16*)dy, dy_cls, cls_stride > 0 ? cls_stride : 1, (const bf16*)z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stats, gamma, (bf16*)dz, nullptr, nullptr, nullptr, dgamma, dbeta, dbias, T, H, (bf16*)dzm, drop, 0); \
+  } while (0)
   DISPATCH_MAXC(H, CALL);
 #undef CALL
   DPRB_LAUNCH_CHECK();
@@ -517,7 +528,7 @@ int embed_ln_bwd(const void* dy, const int64_t* ids, const int64_t* type_ids, co
   if (T == 0) return 0;
   const int grid = grid_for_rows(T);
   const size_t smem = (size_t)WARPS * H * sizeof(float);
-#define CALL(C) ln_bwd_kernel<C, true><<<grid, THREADS, smem, stream>>>((const bf16*)dy, nullptr, 1, nullptr, ids, type_ids, pos_ids, word, pos, type, stats, gamma, nullptr, dword, dpos, dtype, dgamma, dbeta, nullptr, T, H, nullptr, drop, 0)
+#define CALL(C) ln_bwd_kernel<C, true, false><<<grid, THREADS, smem, stream>>>((const bf16*)dy, nullptr, 1, nullptr, ids, type_ids, pos_ids, word, pos, type, stats, gamma, nullptr, dword, dpos, dtype, dgamma, dbeta, nullptr, T, H, nullptr, drop, 0)
   DISPATCH_MAXC(H, CALL);
 #undef CALL
   DPRB_LAUNCH_CHECK();

@@ -547,8 +547,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               for (int c4 = 0; c4 < 4; ++c4) {
                 const int ch = h * 4 + c4;
                 const uint4 q = *reinterpret_cast<const uint4*>(slab + lane * 128 + ((ch ^ (lane & 7)) << 4));
-                const bool af = p.aux_f16 != 0;
-                const float2 f0 = unpack_16x2(q.x, af), f1 = unpack_16x2(q.y, af), f2 = unpack_16x2(q.z, af), f3 = unpack_16x2(q.w, af);
+                float2 f0, f1, f2, f3;
+                if (p.aux_f16) { f0 = unpack_f16x2(q.x); f1 = unpack_f16x2(q.y); f2 = unpack_f16x2(q.z); f3 = unpack_f16x2(q.w); }
+                else { f0 = unpack_bf16x2(q.x); f1 = unpack_bf16x2(q.y); f2 = unpack_bf16x2(q.z); f3 = unpack_bf16x2(q.w); }
                 const float a[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
                 if (p.epilogue == DPRB_EPI_DGELU_PRE) {
                   // aux holds the pre-activation: derivative rebuilt here (same fitted function as the forward)
@@ -571,9 +572,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int c4 = 0; c4 < 4; ++c4) {
               const int ch = h * 4 + c4;
               uint4 q;
-              const bool of = p.out_f16 != 0;
-              q.x = pack_16x2(v[c4 * 8 + 0], v[c4 * 8 + 1], of); q.y = pack_16x2(v[c4 * 8 + 2], v[c4 * 8 + 3], of);
-              q.z = pack_16x2(v[c4 * 8 + 4], v[c4 * 8 + 5], of); q.w = pack_16x2(v[c4 * 8 + 6], v[c4 * 8 + 7], of);
+              if (p.out_f16) {
+                q.x = pack_f16x2(v[c4 * 8 + 0], v[c4 * 8 + 1]); q.y = pack_f16x2(v[c4 * 8 + 2], v[c4 * 8 + 3]);
+                q.z = pack_f16x2(v[c4 * 8 + 4], v[c4 * 8 + 5]); q.w = pack_f16x2(v[c4 * 8 + 6], v[c4 * 8 + 7]);
+              } else {
+                q.x = pack_bf16x2(v[c4 * 8 + 0], v[c4 * 8 + 1]); q.y = pack_bf16x2(v[c4 * 8 + 2], v[c4 * 8 + 3]);
+                q.z = pack_bf16x2(v[c4 * 8 + 4], v[c4 * 8 + 5]); q.w = pack_bf16x2(v[c4 * 8 + 6], v[c4 * 8 + 7]);
+              }
               *reinterpret_cast<uint4*>(slab + lane * 128 + ((ch ^ (lane & 7)) << 4)) = q;
             }
           }

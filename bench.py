@@ -416,9 +416,18 @@ def dataloader_leg(trainer, dev, B, n, S, steps, warmup):
         assert tuple(b["query_ids"]["input_ids"].shape) == (B, S)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        host = torch.empty(steps, dtype=torch.float32).pin_memory()
+        ready = [torch.cuda.Event() for _ in range(steps)]
         e0.record()
-        for i in range(steps):
-            float(trainer.training_step(next(it), i))
+        for i in range(steps):               # loss of step i read while step i+1 runs, as in the e2e leg
+            loss = trainer.training_step(next(it), i)
+            host[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+            ready[i].record()
+            if i > 0:
+                ready[i - 1].synchronize()
+                float(host[i - 1])
+        ready[steps - 1].synchronize()
+        float(host[steps - 1])
         e1.record()
         torch.cuda.synchronize()
         it.close()
@@ -470,12 +479,14 @@ def run_b200(args, workload):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, finish=None):
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
             fn(i)
+        if finish is not None:
+            finish()                     # still inside the timed region
         e1.record()
         sync_all()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -515,14 +526,28 @@ def run_b200(args, workload):
     task.phase_timer = _ScoreCE.phase = None
 
     # ---- end-to-end number: host (pinned) inputs -> H2D each step, loss read back each step
+    # Every step's loss is copied to pinned host memory inside the step and READ one step later (the usual logging lag:
+    # the host enqueues step i+1 while the GPU finishes step i); the last one is read before the timer stops.
     losses = []
+    loss_host = torch.empty(args.steps + 1, dtype=torch.float32).pin_memory()
+    loss_ready = [torch.cuda.Event() for _ in range(args.steps + 1)]
 
-    def e2e_step(i):
+    def read_loss(i):
+        loss_ready[i].synchronize()
+        losses.append(float(loss_host[i]))
+
+    def e2e_step(i, lag=True):
         b = to_device(host_batch, dev)
-        losses.append(float(trainer.training_step(b, i)))  # D2H read of the step's loss
+        loss = trainer.training_step(b, i)
+        loss_host[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)   # D2H of the step's loss
+        loss_ready[i].record()
+        if lag and i > 0:
+            read_loss(i - 1)
 
-    e2e_step(0)
-    ms_e2e = timed(e2e_step, args.steps)
+    e2e_step(args.steps, lag=False)      # one untimed step through the same path (uses the spare slot)
+    read_loss(args.steps)
+    losses.clear()
+    ms_e2e = timed(e2e_step, args.steps, finish=lambda: read_loss(args.steps - 1))
 
     # ---- N > 1: the same step with the bf16-compressed gradient all-reduce (`fp16_grads`, dpr_task.py:90-92)
     alt = None
@@ -587,7 +612,8 @@ def run_b200(args, workload):
                    "grad_allreduce": (args.grad_dtype + (" (reference default: fp16_grads=false)" if args.grad_dtype == "fp32" else " (fp16_grads=true)")) if world > 1 else None,
                    "l2": "working set (>=40 GB activations + 0.9 GB weights/step) exceeds the 126 MB L2; no flush needed"},
         "e2e": {"value": pairs_step / (ms_e2e / 1e3), "unit": "pairs/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": batch_bytes(host_batch), "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": batch_bytes(host_batch), "d2h_bytes_per_step": 4,
+                "d2h": "every step's loss copied to pinned host memory in the step, read by the host one step later"},
         "e2e_dataloader": dl,
         "gpu_launches": launches,
         "gpu_launches_how": "dprb_launch_count(): incremented at every kernel launch inside libdprb.so, difference over the timed region",

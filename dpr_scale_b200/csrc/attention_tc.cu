@@ -136,17 +136,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       tcgen05_fence_after();
       // pass 1: row max (TMEM reads are cheap: re-reading S beats holding 128 scores in registers)
       float m = -INFINITY;
+      const float2 sc2 = make_float2(SCALE_LOG2, SCALE_LOG2);
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
         tmem_ld_32x32(tS + lane_addr + c * 32, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) m = fmaxf(m, fmaf(__uint_as_float(r[j]), SCALE_LOG2, mk[c * 32 + j]));
+        for (int j = 0; j < 32; j += 2) {   // packed fp32 (FFMA2): the softmax passes are issue-bound, not MUFU-bound
+          const float2 a = __ffma2_rn(make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), sc2,
+                                      *reinterpret_cast<const float2*>(mk + c * 32 + j));
+          m = fmaxf(m, fmaxf(a.x, a.y));
+        }
       }
       const float e = (m == -INFINITY) ? 0.f : m;  // fully masked row guard
+      const float2 ne2 = make_float2(-e, -e);
       // pass 2: P = exp2(s - max) -> bf16 -> swizzled smem (A operand of P V), row sum
-      float l = 0.f;
+      float2 l2 = make_float2(0.f, 0.f);
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
@@ -156,25 +162,26 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         for (int c4 = 0; c4 < 4; ++c4) {
           float p[8];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
+          for (int t = 0; t < 8; t += 2) {
             const int j = c4 * 8 + t;
-            p[t] = ex2_approx(fmaf(__uint_as_float(r[j]), SCALE_LOG2, mk[c * 32 + j]) - e);
-            l += p[t];
-          }
-          if (DROP) {
-            // attention-probability dropout (modeling_bert.py: dropout on the softmax output): the row sum keeps
-            // the un-dropped value, only the P V operand is masked and rescaled
-#pragma unroll
-            for (int t = 0; t < 8; t += 2) {
-              float m0, m1;
-              drop.mul2((uint32_t)(prob * S + row), (uint32_t)(c * 32 + c4 * 8 + t), m0, m1);
-              p[t] *= m0; p[t + 1] *= m1;
+            const float2 a = __fadd2_rn(__ffma2_rn(make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), sc2,
+                                                   *reinterpret_cast<const float2*>(mk + c * 32 + j)), ne2);
+            float2 pv = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+            l2 = __fadd2_rn(l2, pv);
+            if (DROP) {
+              // attention-probability dropout (modeling_bert.py: dropout on the softmax output): the row sum keeps
+              // the un-dropped value, only the P V operand is masked and rescaled
+              float2 mm;
+              drop.mul2((uint32_t)(prob * S + row), (uint32_t)(c * 32 + j), mm.x, mm.y);
+              pv = __fmul2_rn(pv, mm);
             }
+            p[t] = pv.x; p[t + 1] = pv.y;
           }
           const int chunk = c * 4 + c4;
           st_chunk(sP + (chunk >> 3) * TILE_BYTES, row, chunk & 7, p, 1.f);
         }
       }
+      const float l = l2.x + l2.y;
       fence_proxy_async_smem();
       tcgen05_fence_before();
       __syncwarp();
@@ -339,9 +346,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       // pass 1 (own 64 columns): P (packed in registers + smem block `half`), partial D_i = sum_j P_ij dP_ij
       // With attention dropout: P_d = P * mask/(1-p) feeds dV; dP arrives w.r.t. P_d, so dP_m = dP * mask/(1-p),
       // D_i = sum_j P_ij dP_m_ij and dS = P (dP_m - D).  The keep bits of this thread's 64 columns live in one register.
+      // (packed fp32 throughout: these passes are bound by instruction issue at the power-capped clock)
       uint32_t pk[32];
       uint64_t keep = ~0ull;
-      float D = 0.f;
+      float2 D2 = make_float2(0.f, 0.f);
+      const float2 sc2 = make_float2(SCALE_LOG2, SCALE_LOG2), nl2 = make_float2(-lse2, -lse2);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t rs[32], rd[32];
@@ -350,37 +359,35 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         tmem_ld_wait();
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
-          float p[8], pd[8];
+          uint32_t qd[4];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const int j = c4 * 8 + t;
-            p[t] = ex2_approx(fmaf(__uint_as_float(rs[j]), SCALE_LOG2, mk[half * 64 + c * 32 + j]) - lse2);
-            pd[t] = p[t];
-          }
-          if (DROP) {
-#pragma unroll
-            for (int t = 0; t < 8; t += 2) {
-              float m0, m1;
-              drop.mul2((uint32_t)(prob * S + row), (uint32_t)(half * 64 + c * 32 + c4 * 8 + t), m0, m1);
-              if (m0 == 0.f) keep &= ~(1ull << (c * 32 + c4 * 8 + t));
-              if (m1 == 0.f) keep &= ~(1ull << (c * 32 + c4 * 8 + t + 1));
-              pd[t] *= m0; pd[t + 1] *= m1;
+          for (int t = 0; t < 4; ++t) {
+            const int j = c4 * 8 + 2 * t;
+            const float2 a = __fadd2_rn(__ffma2_rn(make_float2(__uint_as_float(rs[j]), __uint_as_float(rs[j + 1])), sc2,
+                                                   *reinterpret_cast<const float2*>(mk + half * 64 + c * 32 + j)), nl2);
+            const float2 pv = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+            float2 pdv = pv;
+            if (DROP) {
+              float2 mm;
+              drop.mul2((uint32_t)(prob * S + row), (uint32_t)(half * 64 + c * 32 + j), mm.x, mm.y);
+              if (mm.x == 0.f) keep &= ~(1ull << (c * 32 + j));
+              if (mm.y == 0.f) keep &= ~(1ull << (c * 32 + j + 1));
+              pdv = __fmul2_rn(pv, mm);
             }
+            D2 = __ffma2_rn(pdv, make_float2(__uint_as_float(rd[j]), __uint_as_float(rd[j + 1])), D2);
+            pk[c * 16 + c4 * 4 + t] = pack_bf16x2(pv.x, pv.y);
+            qd[t] = DROP ? pack_bf16x2(pdv.x, pdv.y) : pk[c * 16 + c4 * 4 + t];
           }
-#pragma unroll
-          for (int t = 0; t < 8; ++t) D = fmaf(pd[t], __uint_as_float(rd[c4 * 8 + t]), D);
-#pragma unroll
-          for (int t = 0; t < 4; ++t) pk[c * 16 + c4 * 4 + t] = pack_bf16x2(p[2 * t], p[2 * t + 1]);
           const int chunk = c * 4 + c4;  // 16-byte chunk inside this half's 64-column block
-          uint4 q;
-          q.x = pack_bf16x2(pd[0], pd[1]); q.y = pack_bf16x2(pd[2], pd[3]);
-          q.z = pack_bf16x2(pd[4], pd[5]); q.w = pack_bf16x2(pd[6], pd[7]);
-          *reinterpret_cast<uint4*>(sP + half * TILE_BYTES + row * 128 + ((chunk ^ (row & 7)) << 4)) = q;
+          *reinterpret_cast<uint4*>(sP + half * TILE_BYTES + row * 128 + ((chunk ^ (row & 7)) << 4)) =
+              make_uint4(qd[0], qd[1], qd[2], qd[3]);
         }
       }
+      float D = D2.x + D2.y;
       dpart[half * 128 + row] = D;
       named_bar_sync(2, BWD_CT);
       D = dpart[row] + dpart[128 + row];
+      const float2 nD2 = make_float2(-D, -D);
       // pass 2: dS = P (dP - D) / sqrt(dh)
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -393,14 +400,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const float2 pp = unpack_bf16x2(pk[c * 16 + c4 * 4 + t]);
-            float m0 = 1.f, m1 = 1.f;
+            const float2 dv = make_float2(__uint_as_float(rd[c4 * 8 + 2 * t]), __uint_as_float(rd[c4 * 8 + 2 * t + 1]));
+            float2 inner;
             if (DROP) {
               const int j0 = c * 32 + c4 * 8 + 2 * t;
-              m0 = ((keep >> j0) & 1ull) ? drop.scale : 0.f;
-              m1 = ((keep >> (j0 + 1)) & 1ull) ? drop.scale : 0.f;
+              const float2 mm = make_float2(((keep >> j0) & 1ull) ? drop.scale : 0.f,
+                                            ((keep >> (j0 + 1)) & 1ull) ? drop.scale : 0.f);
+              inner = __ffma2_rn(dv, mm, nD2);
+            } else {
+              inner = __fadd2_rn(dv, nD2);
             }
-            ds[2 * t] = pp.x * (__uint_as_float(rd[c4 * 8 + 2 * t]) * m0 - D);
-            ds[2 * t + 1] = pp.y * (__uint_as_float(rd[c4 * 8 + 2 * t + 1]) * m1 - D);
+            const float2 o = __fmul2_rn(pp, inner);
+            ds[2 * t] = o.x; ds[2 * t + 1] = o.y;
           }
           st_chunk(sdS + half * TILE_BYTES, row, c * 4 + c4, ds, 0.125f);
         }

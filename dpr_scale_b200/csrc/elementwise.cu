@@ -383,6 +383,220 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ dy_cls, int
   }
 }
 
+// ------------------------------------------------------------------ full-width rows: H == MAXC * 256, dense dy
+// The encoder's LayerNorms (H = 768 / 1024, every row has an upstream gradient) take these two kernels.  They do the
+// same arithmetic as ln_fwd_kernel / ln_bwd_kernel on PAIRS of columns with packed fp32 instructions (FADD2 / FMUL2 /
+// FFMA2), without the per-chunk width predicates, and keep gamma / beta in shared memory in a bank-conflict-free
+// layout.  The generic kernels issue 473 (fwd) / 1 132 (bwd) instructions per 768-wide row, more than an SM can issue
+// in the time its share of HBM bandwidth delivers the row (~420 / ~840 issue slots at 6.5 TB/s): they were
+// instruction-bound at ~0.5 of the HBM roofline.
+//
+// Shared-memory layout of a per-column vector v[H] ("pair layout"): chunk i of lane l holds columns c .. c+7 with
+// c = (32 i + l) * 8; columns c..c+3 live at [i*256 + l*4], columns c+4..c+7 at [i*256 + 128 + l*4], so both 16-byte
+// reads of a lane are conflict-free.
+__device__ __forceinline__ int pair_layout(int col) {
+  const int i = col >> 8, r = col & 255, l = r >> 3, j = r & 7;
+  return i * 256 + (j >> 2) * 128 + l * 4 + (j & 3);
+}
+__device__ __forceinline__ void lds8_pairs(const float* base, int i, int lane, float2 (&v)[4]) {
+  const float4 a = *reinterpret_cast<const float4*>(base + i * 256 + lane * 4);
+  const float4 b = *reinterpret_cast<const float4*>(base + i * 256 + 128 + lane * 4);
+  v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w); v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
+}
+__device__ __forceinline__ void unpack8_pairs(const uint4& q, float2 (&v)[4], bool f16) {
+  v[0] = unpack_16x2(q.x, f16); v[1] = unpack_16x2(q.y, f16); v[2] = unpack_16x2(q.z, f16); v[3] = unpack_16x2(q.w, f16);
+}
+
+template <int MAXC, bool ZF16>
+__global__ void __launch_bounds__(THREADS, 4)
+ln_fwd_full_kernel(const bf16* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   bf16* __restrict__ y, bf16* __restrict__ y_res, float* __restrict__ stats,
+                   float* __restrict__ cls_out, int cls_stride, int T, float eps) {
+  constexpr int H = MAXC * 256;
+  __shared__ __align__(16) float s_g[H];
+  __shared__ __align__(16) float s_b[H];
+  for (int i = threadIdx.x; i < H; i += THREADS) { s_g[pair_layout(i)] = gamma[i]; s_b[pair_layout(i)] = beta[i]; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * WARPS;
+  for (int row = warp_global; row < T; row += nwarps) {
+    const uint4* zr = reinterpret_cast<const uint4*>(z + (long long)row * H) + lane;
+    uint4 q[MAXC];
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) q[i] = ldg_nc_v4(zr + 32 * i);
+    float2 x[MAXC][4];
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) unpack8_pairs(q[i], x[i], ZF16);
+    float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s = __fadd2_rn(s, x[i][k]);
+    const float mean = warp_sum(s.x + s.y) / (float)H;
+    const float2 nm = make_float2(-mean, -mean);
+    float2 qq = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { x[i][k] = __fadd2_rn(x[i][k], nm); qq = __ffma2_rn(x[i][k], x[i][k], qq); }
+    const float var = warp_sum(qq.x + qq.y) / (float)H;
+    const float rstd = rsqrtf(var + eps);
+    const float2 r2 = make_float2(rstd, rstd);
+    const bool is_cls = (cls_out != nullptr) && (row % cls_stride == 0);
+    uint4* yr = reinterpret_cast<uint4*>(y + (long long)row * H) + lane;
+    uint4* yres = y_res ? reinterpret_cast<uint4*>(y_res + (long long)row * H) + lane : nullptr;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      float2 g[4], b[4], o[4];
+      lds8_pairs(s_g, i, lane, g);
+      lds8_pairs(s_b, i, lane, b);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = __ffma2_rn(__fmul2_rn(x[i][k], r2), g[k], b[k]);
+      yr[32 * i] = make_uint4(pack_bf16x2(o[0].x, o[0].y), pack_bf16x2(o[1].x, o[1].y), pack_bf16x2(o[2].x, o[2].y),
+                              pack_bf16x2(o[3].x, o[3].y));
+      if (yres != nullptr)
+        yres[32 * i] = make_uint4(pack_f16x2(o[0].x, o[0].y), pack_f16x2(o[1].x, o[1].y), pack_f16x2(o[2].x, o[2].y),
+                                  pack_f16x2(o[3].x, o[3].y));
+      if (is_cls) {
+        float* co = cls_out + (long long)(row / cls_stride) * H + (lane + 32 * i) * 8;
+        *reinterpret_cast<float4*>(co) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+        *reinterpret_cast<float4*>(co + 4) = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
+      }
+    }
+    if (lane == 0) *reinterpret_cast<float2*>(stats + 2 * (long long)row) = make_float2(mean, rstd);
+  }
+}
+
+template <int MAXC, bool ZF16>
+__global__ void __launch_bounds__(THREADS)
+ln_bwd_full_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, const float* __restrict__ stats,
+                   const float* __restrict__ gamma, bf16* __restrict__ dz, float* __restrict__ dgamma,
+                   float* __restrict__ dbeta, float* __restrict__ dbias, int T, bf16* __restrict__ dzm, Drop drop) {
+  constexpr int H = MAXC * 256;
+  constexpr int SLOT_BYTES = 2 * MAXC * 512 + 16;  // z chunks | dy chunks | (mean, rstd)
+  constexpr int RING_BYTES = WARPS * PF_DEPTH * SLOT_BYTES;
+  constexpr int FLUSH_BYTES = WARPS * H * 4;
+  constexpr int FRONT_BYTES = RING_BYTES > FLUSH_BYTES ? RING_BYTES : FLUSH_BYTES;
+  extern __shared__ float smem_f[];
+  float* s_g = smem_f + FRONT_BYTES / 4;           // gamma in pair layout, behind the ring / flush area
+  for (int i = threadIdx.x; i < H; i += THREADS) s_g[pair_layout(i)] = gamma[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * WARPS;
+  float2 ag[MAXC][4], ab[MAXC][4], az[MAXC][4];
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { ag[i][k] = make_float2(0.f, 0.f); ab[i][k] = ag[i][k]; az[i][k] = ag[i][k]; }
+  // per-lane FIFO of the next PF_DEPTH rows (see ln_bwd_kernel)
+  uint8_t* ring = reinterpret_cast<uint8_t*>(smem_f) + (size_t)(threadIdx.x >> 5) * PF_DEPTH * SLOT_BYTES;
+  auto stage = [&](int r, int slot) {
+    if (r < T) {
+      const bf16* zs = z + (long long)r * H + lane * 8;
+      const bf16* ds = dy + (long long)r * H + lane * 8;
+      uint8_t* dst = ring + slot * SLOT_BYTES + lane * 16;
+#pragma unroll
+      for (int i = 0; i < MAXC; ++i) {
+        cp_async_16(dst + i * 512, zs + i * 256);
+        cp_async_16(dst + (MAXC + i) * 512, ds + i * 256);
+      }
+      if (lane == 0) cp_async_8(ring + slot * SLOT_BYTES + 2 * MAXC * 512, stats + 2 * (long long)r);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int d = 0; d < PF_DEPTH - 1; ++d) stage(warp_global + d * nwarps, d);
+  const bool do_drop = (dzm != nullptr);
+  const bool do_bias = (dbias != nullptr);
+  int slot = 0;
+  for (int row = warp_global; row < T; row += nwarps) {
+    stage(row + (PF_DEPTH - 1) * nwarps, (slot + PF_DEPTH - 1) % PF_DEPTH);
+    cp_async_wait<PF_DEPTH - 1>();
+    const uint8_t* src = ring + slot * SLOT_BYTES + lane * 16;
+    uint4 cz[MAXC], cdy[MAXC];
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      cz[i] = *reinterpret_cast<const uint4*>(src + i * 512);
+      cdy[i] = *reinterpret_cast<const uint4*>(src + (MAXC + i) * 512);
+    }
+    __syncwarp();  // lane 0's (mean, rstd) copy must be visible to the whole warp
+    const float2 st = *reinterpret_cast<const float2*>(ring + slot * SLOT_BYTES + 2 * MAXC * 512);
+    slot = (slot + 1) % PF_DEPTH;
+    const float mean = st.x, rstd = st.y;
+    const float2 nm = make_float2(-mean, -mean), r2 = make_float2(rstd, rstd);
+    float2 xh[MAXC][4], d[MAXC][4];
+    float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      float2 g[4];
+      lds8_pairs(s_g, i, lane, g);
+      unpack8_pairs(cz[i], xh[i], ZF16);
+      unpack8_pairs(cdy[i], d[i], false);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        xh[i][k] = __fmul2_rn(__fadd2_rn(xh[i][k], nm), r2);
+        ag[i][k] = __ffma2_rn(d[i][k], xh[i][k], ag[i][k]);
+        ab[i][k] = __fadd2_rn(ab[i][k], d[i][k]);
+        d[i][k] = __fmul2_rn(d[i][k], g[k]);       // dxhat
+        s1 = __fadd2_rn(s1, d[i][k]);
+        s2 = __ffma2_rn(d[i][k], xh[i][k], s2);
+      }
+    }
+    const float m1 = warp_sum(s1.x + s1.y) / (float)H;
+    const float m2 = warp_sum(s2.x + s2.y) / (float)H;
+    const float2 nm1 = make_float2(-m1, -m1), nm2 = make_float2(-m2, -m2);
+    uint4* dzr = reinterpret_cast<uint4*>(dz + (long long)row * H) + lane;
+    uint4* dzmr = do_drop ? reinterpret_cast<uint4*>(dzm + (long long)row * H) + lane : nullptr;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      float2 o[4];
+      uint32_t w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        o[k] = __fmul2_rn(r2, __fadd2_rn(__ffma2_rn(xh[i][k], nm2, d[i][k]), nm1));   // rstd * (d - s1 - xh * s2)
+        w[k] = pack_bf16x2(o[k].x, o[k].y);
+      }
+      dzr[32 * i] = make_uint4(w[0], w[1], w[2], w[3]);
+      if (do_drop) {
+        // hidden dropout sat between the Linear and this residual+LayerNorm: the Linear's output gradient is
+        // dz * mask / (1-p) (second output), while the residual branch takes dz itself
+        const uint32_t c = (uint32_t)(lane + 32 * i) * 8u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float2 m;
+          drop.mul2((uint32_t)row, c + 2u * k, m.x, m.y);
+          const float2 om = __fmul2_rn(o[k], m);
+          w[k] = pack_bf16x2(om.x, om.y);
+        }
+        dzmr[32 * i] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      if (do_bias) {
+        // the Linear's bias gradient: column sums of ITS output gradient (the masked copy when dropout is on), as the
+        // bf16-rounded values the downstream GEMMs consume
+#pragma unroll
+        for (int k = 0; k < 4; ++k) az[i][k] = __fadd2_rn(az[i][k], unpack_bf16x2(w[k]));
+      }
+    }
+  }
+  cp_async_wait<0>();
+  bool act[MAXC];
+  float t[MAXC][8];
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) act[i] = true;
+  auto flush = [&](float2 (&a)[MAXC][4], float* out) {
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { t[i][2 * k] = a[i][k].x; t[i][2 * k + 1] = a[i][k].y; }
+    flush_cols<MAXC>(t, act, smem_f, out, H);
+  };
+  flush(ag, dgamma);
+  flush(ab, dbeta);
+  if (do_bias) flush(az, dbias);
+}
+
 // ------------------------------------------------------------------ column sums (bias gradients)
 __global__ void __launch_bounds__(THREADS)
 colsum_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ out, int T, int N, int rows_per_cta) {
@@ -447,6 +661,12 @@ int grid_for_rows(int T) {
     else if (_c == 3) { CALL(3); } else { CALL(4); }              \
   } while (0)
 
+// A/B aid for tools/ln_bench.py: DPRB_LN_GENERIC=1 sends full-width rows through the generic kernels too.
+static bool ln_generic_forced() {
+  const char* e = getenv("DPRB_LN_GENERIC");
+  return e != nullptr && e[0] == '1';
+}
+
 static int check_h(int H, const char* who) {
   DPRB_REQUIRE(H > 0 && H % 8 == 0 && H <= 1024, "%s: hidden size %d unsupported (need H %% 8 == 0, H <= 1024)", who, H);
   return 0;
@@ -474,6 +694,17 @@ int ln_fwd(const void* z, const float* gamma, const float* beta, void* y, float*
   if (T == 0) return 0;
   DPRB_REQUIRE(cls_out == nullptr || cls_stride > 0, "ln_fwd: cls_stride must be positive");
   const int grid = grid_for_rows(T);
+  if (H % 256 == 0 && !ln_generic_forced()) {   // full-width rows (the encoder's H = 768 / 1024): packed-fp32 kernel
+#define CALLF(C)                                                                                                         \
+  do {                                                                                                                   \
+    if (z_f16) ln_fwd_full_kernel<C, true><<<grid, THREADS, 0, stream>>>((const bf16*)z, gamma, beta, (bf16*)y, (bf16*)y_res, stats, cls_out, cls_stride > 0 ? cls_stride : 1, T, eps); \
+    else ln_fwd_full_kernel<C, false><<<grid, THREADS, 0, stream>>>((const bf16*)z, gamma, beta, (bf16*)y, (bf16*)y_res, stats, cls_out, cls_stride > 0 ? cls_stride : 1, T, eps); \
+  } while (0)
+    DISPATCH_MAXC(H, CALLF);
+#undef CALLF
+    DPRB_LAUNCH_CHECK();
+    return 0;
+  }
 #define CALL(C)                                                                                                          \
   do {                                                                                                                   \
     if (z_f16) ln_fwd_kernel<C, false, true><<<grid, THREADS, 0, stream>>>((const bf16*)z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, gamma, beta, (bf16*)y, (bf16*)y_res, stats, cls_out, cls_stride > 0 ? cls_stride : 1, T, H, eps, Drop{0u, 0u, 1.f, 1u}, 1); \
@@ -496,6 +727,30 @@ int ln_bwd(const void* dy, const float* dy_cls, int cls_stride, const void* z, c
   DPRB_REQUIRE(dy_cls == nullptr || cls_stride > 0, "ln_bwd: cls_stride must be positive");
   const int grid = grid_for_rows(T);
   const int maxc = (H + 255) / 256;
+  if (dy != nullptr && H % 256 == 0 && !ln_generic_forced()) {   // dense upstream gradient, full-width rows: packed-fp32 kernel
+    size_t front = (size_t)WARPS * H * sizeof(float);
+    const size_t ring_f = (size_t)WARPS * PF_DEPTH * (2 * maxc * 512 + 16);
+    if (ring_f > front) front = ring_f;
+    const size_t smem_f = front + (size_t)H * sizeof(float);
+    static bool attr_f = false;
+    if (!attr_f) {
+#define SET_ATTR_F(C)                                                                                                                    \
+    DPRB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_full_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024)); \
+    DPRB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_full_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024));
+      SET_ATTR_F(1) SET_ATTR_F(2) SET_ATTR_F(3) SET_ATTR_F(4)
+#undef SET_ATTR_F
+      attr_f = true;
+    }
+#define CALLF(C)                                                                                                         \
+  do {                                                                                                                   \
+    if (z_f16) ln_bwd_full_kernel<C, true><<<grid, THREADS, smem_f, stream>>>((const bf16*)dy, (const bf16*)z, stats, gamma, (bf16*)dz, dgamma, dbeta, dbias, T, (bf16*)dzm, drop); \
+    else ln_bwd_full_kernel<C, false><<<grid, THREADS, smem_f, stream>>>((const bf16*)dy, (const bf16*)z, stats, gamma, (bf16*)dz, dgamma, dbeta, dbias, T, (bf16*)dzm, drop); \
+  } while (0)
+    DISPATCH_MAXC(H, CALLF);
+#undef CALLF
+    DPRB_LAUNCH_CHECK();
+    return 0;
+  }
   size_t smem = (size_t)WARPS * H * sizeof(float);
   const size_t ring = (size_t)WARPS * PF_DEPTH * (2 * maxc * 512 + 16);
   if (ring > smem) smem = ring;

@@ -183,6 +183,19 @@ def check_ln(T=777, H=768, cls_stride=0, seed=1, f16=False):
     _close("ln_dgamma", dgamma, gr.grad, 1e-4, 1e-3, res)
     _close("ln_dbeta", dbeta, br.grad, 1e-4, 1e-3, res)
     _close("ln_dbias", dbias, dz.float().cpu().sum(0), 1e-4, 1e-3, res)
+    if not cls_stride:
+        # hidden dropout between the Linear and this LayerNorm: second output dz * mask / (1-p), and the bias gradient
+        # is the column sum of THAT (the Linear's own output gradient)
+        p_drop, seed0, layer, site = 0.1, 11, 2, 3
+        dg2, db2, dbias2 = (torch.zeros(H, device=DEV) for _ in range(3))
+        dz2, dzm = ops.ln_bwd(dy.to(DEV), z.to(DEV), stats, gamma.to(DEV), dg2, db2, dbias2, None, 1, p_drop,
+                              ops.dropout_site_seed(seed0, layer, site))
+        keep = ops.dropout_mask(T, H, p_drop, seed0, layer, site).float()
+        scale = 1.0 / (1.0 - round(p_drop * 65536) / 65536.0)
+        assert torch.equal(dz2, dz), "ln_bwd: dz must not depend on the dropout site"
+        _close("ln_drop_dzm", dzm, dz.float() * keep * scale, 2 ** -7, 1e-3, res)
+        _close("ln_drop_dbias", dbias2, dzm.float().cpu().sum(0), 1e-4, 1e-3, res)
+        _close("ln_drop_dgamma", dg2, gr.grad, 1e-4, 1e-3, res)
     return res
 
 

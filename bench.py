@@ -567,7 +567,7 @@ def run_b200(args, workload):
             ms_dl = dataloader_leg(trainer, dev, B, n, S, args.steps, args.warmup)
             dl = {"value": B / (ms_dl / 1e3), "unit": "pairs/s", "ms_per_step": ms_dl,
                   "what": "synthetic DPR-format JSONL -> dpr_scale_b200.datamodule (background assembly, Rust tokeniser, "
-                          "pinned + side-stream H2D) -> training_step, loss read back every step",
+                          "pinned + side-stream H2D) -> training_step, loss copied to pinned memory every step and read one step later",
                   "host_threads": usable_cores()}
         except Exception as e:  # noqa: the headline numbers above must survive a data-side failure
             dl = {"error": repr(e)[:300]}

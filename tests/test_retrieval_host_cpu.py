@@ -71,7 +71,7 @@ def test_main_flow_with_emulated_search(tmp_path, monkeypatch):
 
     from dpr_scale_b200 import ops
 
-    def fake_search(q, c, k, index_offset=0):
+    def fake_search(q, c, k, index_offset=0, reference_ranking=False):
         s = q.float() @ c.float().T
         v, i = torch.sort(s, dim=1, descending=True, stable=True)
         return v[:, :k].contiguous(), i[:, :k] + index_offset

@@ -161,6 +161,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
           float p[8];
+          float2 mm4[4];
+          if (DROP) drop.mul8((uint32_t)(prob * S + row), (uint32_t)(c * 32 + c4 * 8), mm4);
 #pragma unroll
           for (int t = 0; t < 8; t += 2) {
             const int j = c4 * 8 + t;
@@ -171,9 +173,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             if (DROP) {
               // attention-probability dropout (modeling_bert.py: dropout on the softmax output): the row sum keeps
               // the un-dropped value, only the P V operand is masked and rescaled
-              float2 mm;
-              drop.mul2((uint32_t)(prob * S + row), (uint32_t)(c * 32 + j), mm.x, mm.y);
-              pv = __fmul2_rn(pv, mm);
+              pv = __fmul2_rn(pv, mm4[t >> 1]);
             }
             p[t] = pv.x; p[t + 1] = pv.y;
           }
@@ -360,6 +360,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
           uint32_t qd[4];
+          float2 mm4[4];
+          if (DROP) drop.mul8((uint32_t)(prob * S + row), (uint32_t)(half * 64 + c * 32 + c4 * 8), mm4);
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const int j = c4 * 8 + 2 * t;
@@ -368,8 +370,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             const float2 pv = make_float2(ex2_approx(a.x), ex2_approx(a.y));
             float2 pdv = pv;
             if (DROP) {
-              float2 mm;
-              drop.mul2((uint32_t)(prob * S + row), (uint32_t)(half * 64 + c * 32 + j), mm.x, mm.y);
+              const float2 mm = mm4[t];
               if (mm.x == 0.f) keep &= ~(1ull << (c * 32 + j));
               if (mm.y == 0.f) keep &= ~(1ull << (c * 32 + j + 1));
               pdv = __fmul2_rn(pv, mm);

@@ -155,10 +155,11 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             }
             if (DROP) {
 #pragma unroll
-              for (int t = 0; t < 8; t += 2) {
-                float m0, m1;
-                drop.mul2((uint32_t)(prob * S + grow), (uint32_t)(c * 32 + c4 * 8 + t), m0, m1);
-                p[t] *= m0; p[t + 1] *= m1;
+              for (int t = 0; t < 8; t += 8) {
+                float2 m[4];
+                drop.mul8((uint32_t)(prob * S + grow), (uint32_t)(c * 32 + c4 * 8), m);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) { p[2 * w] *= m[w].x; p[2 * w + 1] *= m[w].y; }
               }
             }
             const int chunk = c * 4 + c4;  // 16-byte chunk index over the 256 key columns
@@ -377,11 +378,14 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
               }
               if (DROP) {
 #pragma unroll
-                for (int t = 0; t < 8; t += 2) {
-                  float m0, m1;
-                  drop.mul2((uint32_t)(prob * S + grow), (uint32_t)(j * 128 + half * 64 + c * 32 + c4 * 8 + t), m0, m1);
-                  pd[t] *= m0; pd[t + 1] *= m1;
-                  ds[t] *= m0; ds[t + 1] *= m1;
+                for (int t = 0; t < 8; t += 8) {
+                  float2 m[4];
+                  drop.mul8((uint32_t)(prob * S + grow), (uint32_t)(j * 128 + half * 64 + c * 32 + c4 * 8), m);
+#pragma unroll
+                  for (int w = 0; w < 4; ++w) {
+                    pd[2 * w] *= m[w].x; pd[2 * w + 1] *= m[w].y;
+                    ds[2 * w] *= m[w].x; ds[2 * w + 1] *= m[w].y;
+                  }
                 }
               }
 #pragma unroll

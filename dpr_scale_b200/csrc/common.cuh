@@ -143,7 +143,7 @@ __device__ __forceinline__ void gelu_and_grad2(float2 x, float2& g, float2& gd) 
   gd = __fmul2_rn(sg, w);
 }
 // Counter-based dropout RNG.  One 32-bit hash (lowbias32 finaliser, 9 integer instructions) decides TWO horizontally
-// adjacent elements (16 bits each), keyed by (row, column pair, site seed): element (r, c) is kept iff its 16-bit lane
+// adjacent elements (16 bits each), keyed by (row, column group of 8, pair in the group, site seed): element (r, c) is kept iff its 16-bit lane
 // is >= thresh16 = round(p * 65536); kept values are scaled by 1 / (1 - thresh16/65536) (p = 0.1 -> 0.100006).
 // thresh16 == 0 disables the site (p = 0 / eval mode).  Masks are never stored: backward re-derives them.
 struct Drop {
@@ -152,16 +152,36 @@ struct Drop {
   float scale;
   uint32_t row_mul;  // row key = r * row_mul (the pruned last layer runs on the CLS rows only: key = row * S)
   __host__ __device__ bool on() const { return thresh16 != 0u; }
-  __device__ __forceinline__ uint32_t pair_hash(uint32_t r, uint32_t c_even) const {
-    uint32_t x = (r * row_mul) * 0x9E3779B1u + (c_even >> 1) * 0x85EBCA6Bu + seed;
-    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  // One hash chain per GROUP OF 8 columns: a shared first round keyed by (row, column / 8, site seed), then one cheap
+  // finaliser per column pair (four odd multipliers).  A quarter of the mixing work of a full hash per pair - the
+  // dropout epilogues, the LayerNorm backward and the attention passes are all bound by instruction issue.
+  __device__ __forceinline__ uint32_t group_mix(uint32_t r, uint32_t c8) const {   // c8 = column / 8
+    uint32_t x = (r * row_mul) * 0x9E3779B1u + c8 * 0x85EBCA6Bu + seed;
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15;
     return x;
+  }
+  __device__ __forceinline__ static uint32_t pair_word(uint32_t x, uint32_t w) {  // w = pair index 0..3 in the group
+    const uint32_t k = w == 0u ? 0x846CA68Bu : (w == 1u ? 0xC2B2AE35u : (w == 2u ? 0x27D4EB2Fu : 0x165667B1u));
+    uint32_t h = x * k;
+    h ^= h >> 16;
+    return h;
+  }
+  __device__ __forceinline__ uint32_t pair_hash(uint32_t r, uint32_t c_even) const {
+    return pair_word(group_mix(r, c_even >> 3), (c_even >> 1) & 3u);
+  }
+  __device__ __forceinline__ void lanes(uint32_t h, float& m0, float& m1) const {
+    m0 = (h & 0xFFFFu) >= thresh16 ? scale : 0.f;
+    m1 = (h >> 16) >= thresh16 ? scale : 0.f;
   }
   // multipliers (scale or 0) for elements (r, c_even) and (r, c_even + 1); c_even must be even
   __device__ __forceinline__ void mul2(uint32_t r, uint32_t c_even, float& m0, float& m1) const {
-    const uint32_t h = pair_hash(r, c_even);
-    m0 = (h & 0xFFFFu) >= thresh16 ? scale : 0.f;
-    m1 = (h >> 16) >= thresh16 ? scale : 0.f;
+    lanes(pair_hash(r, c_even), m0, m1);
+  }
+  // the same multipliers for the 8 columns c0 .. c0+7 (c0 a multiple of 8) as four pairs: one group_mix for all
+  __device__ __forceinline__ void mul8(uint32_t r, uint32_t c0, float2 (&m)[4]) const {
+    const uint32_t x = group_mix(r, c0 >> 3);
+#pragma unroll
+    for (int w = 0; w < 4; ++w) lanes(pair_word(x, (uint32_t)w), m[w].x, m[w].y);
   }
 };
 inline Drop make_drop(float p, uint64_t seed, int layer, int site) {

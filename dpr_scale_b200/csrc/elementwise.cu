@@ -143,10 +143,11 @@ ln_fwd_kernel(const bf16* __restrict__ z, const int64_t* __restrict__ ids, const
         for (int j = 0; j < 8; ++j) o[j] = (x[i][j] - mean) * rstd * g8[j] + b8[j];
         if (EMBED && drop.on()) {  // embedding dropout (modeling_bert.py:111)
 #pragma unroll
-          for (int j = 0; j < 8; j += 2) {
-            float m0, m1;
-            drop.mul2((uint32_t)row, (uint32_t)(c + j), m0, m1);
-            o[j] *= m0; o[j + 1] *= m1;
+          for (int j = 0; j < 8; j += 8) {
+            float2 m[4];
+            drop.mul8((uint32_t)row, (uint32_t)c, m);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) { o[2 * w] *= m[w].x; o[2 * w + 1] *= m[w].y; }
           }
         }
         store8(y + (long long)row * H + c, o);
@@ -311,10 +312,11 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ dy_cls, int
         else load8(dy + (long long)row * H + c, d[i]);
         if (EMBED && drop.on()) {  // upstream gradient is w.r.t. the dropped embedding output
 #pragma unroll
-          for (int j = 0; j < 8; j += 2) {
-            float m0, m1;
-            drop.mul2((uint32_t)row, (uint32_t)(c + j), m0, m1);
-            d[i][j] *= m0; d[i][j + 1] *= m1;
+          for (int j = 0; j < 8; j += 8) {
+            float2 m[4];
+            drop.mul8((uint32_t)row, (uint32_t)c, m);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) { d[i][2 * w] *= m[w].x; d[i][2 * w + 1] *= m[w].y; }
           }
         }
 #pragma unroll
@@ -355,10 +357,11 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ dy_cls, int
             // hidden dropout sat between the Linear and this residual+LayerNorm: the Linear's output gradient is
             // dz * mask / (1-p) (second output), while the residual branch takes dz itself
 #pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-              float m0, m1;
-              drop.mul2((uint32_t)row, (uint32_t)(c + j), m0, m1);
-              o[j] *= m0; o[j + 1] *= m1;
+            for (int j = 0; j < 8; j += 8) {
+              float2 m[4];
+              drop.mul8((uint32_t)row, (uint32_t)c, m);
+#pragma unroll
+              for (int w = 0; w < 4; ++w) { o[2 * w] *= m[w].x; o[2 * w + 1] *= m[w].y; }
             }
             store8(dzm + (long long)row * H + c, o);
           }
@@ -562,12 +565,11 @@ ln_bwd_full_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, cons
       if (do_drop) {
         // hidden dropout sat between the Linear and this residual+LayerNorm: the Linear's output gradient is
         // dz * mask / (1-p) (second output), while the residual branch takes dz itself
-        const uint32_t c = (uint32_t)(lane + 32 * i) * 8u;
+        float2 m[4];
+        drop.mul8((uint32_t)row, (uint32_t)(lane + 32 * i) * 8u, m);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          float2 m;
-          drop.mul2((uint32_t)row, c + 2u * k, m.x, m.y);
-          const float2 om = __fmul2_rn(o[k], m);
+          const float2 om = __fmul2_rn(o[k], m[k]);
           w[k] = pack_bf16x2(om.x, om.y);
         }
         dzmr[32 * i] = make_uint4(w[0], w[1], w[2], w[3]);

@@ -536,10 +536,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               // hidden dropout between the dense layer and the residual add (training only; kept out of the hot
               // loops below so the p = 0 path compiles exactly as before)
 #pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                float m0, m1;
-                p.drop.mul2((uint32_t)row, (uint32_t)(col0 + j), m0, m1);
-                v[j] *= m0; v[j + 1] *= m1;
+              for (int j = 0; j < 32; j += 8) {
+                float2 m[4];
+                p.drop.mul8((uint32_t)row, (uint32_t)(col0 + j), m);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) { v[j + 2 * w] *= m[w].x; v[j + 2 * w + 1] *= m[w].y; }
               }
             }
             if (has_aux) {

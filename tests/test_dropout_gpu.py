@@ -79,3 +79,27 @@ def test_dropout_is_off_in_eval_and_reseeds_each_forward():
     c, d = enc(tokens).detach(), enc(tokens).detach()
     assert not torch.equal(c, d)  # fresh masks per forward
     assert rel_l2(c, a) > 1e-2
+
+
+def test_mask_statistics():
+    """The counter-based masks (one hash chain per 8 columns, a finaliser per column pair: csrc/common.cuh Drop) behave
+    like independent Bernoulli(1 - p) draws: keep rate, and no correlation between neighbouring columns (same pair, same
+    group, next group), neighbouring rows, or two sites / layers of the same seed."""
+    from dpr_scale_b200 import ops
+    rows, cols, p = 4096, 768, 0.1
+    m = ops.dropout_mask(rows, cols, p, 5, 3, 2).float()
+    assert abs(float(m.mean()) - (1 - p)) < 2e-3, float(m.mean())
+    per_col = m.mean(0)
+    assert float((per_col - (1 - p)).abs().max()) < 0.03          # 4096 draws per column: sigma = 0.0047
+
+    def corr(a, b):
+        a, b = a - a.mean(), b - b.mean()
+        return float((a * b).mean() / (a.std() * b.std()))
+
+    other_site = ops.dropout_mask(rows, cols, p, 5, 3, 3).float()
+    other_layer = ops.dropout_mask(rows, cols, p, 5, 4, 2).float()
+    pairs = {"same pair": (m[:, 0::2], m[:, 1::2]), "next pair": (m[:, :-2], m[:, 2:]), "next group": (m[:, :-8], m[:, 8:]),
+             "next row": (m[:-1], m[1:]), "other site": (m, other_site), "other layer": (m, other_layer)}
+    for name, (a, b) in pairs.items():
+        assert abs(corr(a, b)) < 5e-3, (name, corr(a, b))          # sigma of the estimate: 6e-4
+    assert not torch.equal(m, other_site) and not torch.equal(m, other_layer)

@@ -289,9 +289,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       int it = 0;
       for (int prob = blockIdx.x; prob < nprob; prob += gridDim.x, ++it) {
         const int buf = it & 1;
-        // the previous problem's epilogue (staged in the other buffer) must have drained before that buffer is reloaded
-        if (it > 0) mbar_wait(b_free, (it - 1) & 1);
-        if (prob + (int)gridDim.x < nprob) issue_loads(prob + gridDim.x, buf ^ 1);
+        // This problem's inputs were requested one iteration ago, and the S / dP columns of TMEM are free since the
+        // previous problem's dS pass (b_p): issue S = Q K^T and dP = dO V^T NOW, so they run under the previous
+        // problem's epilogue (which reads only the dV / dK / dQ columns and writes the OTHER input buffer) instead of
+        // after it.
         mbar_wait(&b_load[buf], (it >> 1) & 1);
         tcgen05_fence_after();
         uint8_t* sQ = sIn + buf * 4 * TILE_BYTES;
@@ -303,6 +304,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_f16(tdP, ddo + 2 * k, dv + 2 * k, idesc_s, k > 0);
         umma_commit(b_s);
+        // the previous problem's epilogue (staged in the other buffer) must have drained before that buffer is reloaded
+        if (it > 0) mbar_wait(b_free, (it - 1) & 1);
+        if (prob + (int)gridDim.x < nprob) issue_loads(prob + gridDim.x, buf ^ 1);
         mbar_wait(b_p, it & 1);
         tcgen05_fence_after();
         // transposed A operands: the [i][j] tiles read MN-major (M = j: two 64-wide atoms 16 KB apart; K = i)

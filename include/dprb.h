@@ -118,8 +118,10 @@ int dprb_ln_bwd(const void* dy_bf16, const float* dy_cls, int cls_stride, const 
                 float* dbias, int T, int H, void* dzm_bf16, float dropout_p, uint64_t dropout_site_seed,
                 int z_f16, dprb_stream_t stream);
 /* Dropout sites: 0 embeddings [T,H], 1 attention probabilities [nseq*heads*S, S], 2 attention-output dense [T,H],
- * 3 FFN-output dense [T,H].  Element (r, c) of a site is kept iff a 16-bit lane of hash32(r, c/2, site seed) is
- * >= round(p * 65536); site seed = fold32(dropout_seed + (layer*8 + site + 1) * 0x9E3779B97F4A7C15).
+ * 3 FFN-output dense [T,H].  Element (r, c) of a site is kept iff its 16-bit lane of h(r, c/8, (c/2)%4, site seed)
+ * is >= round(p * 65536) - one hash chain per group of 8 columns, one multiply-xorshift finaliser per column pair
+ * (csrc/common.cuh: Drop); site seed = fold32(dropout_seed + (layer*8 + site + 1) * 0x9E3779B97F4A7C15).
+ * dprb_ln_bwd: dbias accumulates the column sums of the Linear's own output gradient (dzm when dropout is on).
  * dprb_dropout_mask materialises keep[r * cols + c] of one site (test aid). */
 uint64_t dprb_dropout_site_seed(uint64_t dropout_seed, int layer, int site);
 int dprb_dropout_mask(uint8_t* keep, int64_t rows, int cols, float dropout_p, uint64_t dropout_seed, int layer,

@@ -103,3 +103,17 @@ def test_mask_statistics():
     for name, (a, b) in pairs.items():
         assert abs(corr(a, b)) < 5e-3, (name, corr(a, b))          # sigma of the estimate: 6e-4
     assert not torch.equal(m, other_site) and not torch.equal(m, other_layer)
+
+
+def test_masks_equal_host_restatement():
+    """dprb_dropout_mask (the same `Drop` every kernel uses) against oracle/dropout.py, bit for bit: several shapes
+    (incl. widths that are not multiples of 8), probabilities, 64-bit seeds, layers and sites."""
+    from dpr_scale_b200 import ops
+    from oracle import dropout as od
+    cases = [(64, 768, 0.1, 7, 0, 0), (300, 128, 0.1, 7, 11, 1), (33, 1024, 0.5, 2 ** 63 + 12345, 23, 2),
+             (257, 100, 0.25, 0xDEADBEEFCAFE, 5, 3), (5, 6, 0.9, 1, 0, 1), (1000, 3072, 0.1, 99, 2, 3)]
+    for rows, cols, p, seed, layer, site in cases:
+        got = ops.dropout_mask(rows, cols, p, seed, layer, site).cpu().numpy()
+        want = od.keep_mask(rows, cols, p, seed, layer, site)
+        assert (got == want).all(), (rows, cols, p, seed, layer, site, int((got != want).sum()))
+    assert ops.dropout_site_seed(2 ** 63 + 12345, 23, 2) == od.site_seed32(2 ** 63 + 12345, 23, 2)
